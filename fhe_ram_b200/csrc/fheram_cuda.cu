@@ -1,0 +1,1020 @@
+// fheram_cuda.cu -- host side of libfheram_cuda.so: device contexts, HBM-resident keys /
+// addresses / RAM, and the launch schedules of read / read_prepare_write / write.
+// Mirrors (not copies) the control flow of the reference's src/ram.rs; every schedule step
+// cites the lines it reproduces.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fheram.h"
+#include "kernels.cuh"
+
+using namespace fheram;
+
+// --------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+extern "C" const char* fheram_last_error(void) { return g_err.c_str(); }
+extern "C" const char* fheram_version(void) { return "fheram-b200 0.1 (sm_100a)"; }
+void fheram_set_error(const char* msg) { g_err = msg; }
+
+#define CU(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess)                                                            \
+      return fail(FHERAM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x,            \
+                  cudaGetErrorString(e_));                                            \
+  } while (0)
+#define TRY(x)            \
+  do {                    \
+    int rc_ = (x);        \
+    if (rc_) return rc_;  \
+  } while (0)
+
+// --------------------------------------------------------------------------------------
+// parameters / derived sizes
+// --------------------------------------------------------------------------------------
+static int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct Derived {
+  int n, log_n, size_ct, dnum_ct, size_addr, size_evk_trace, dnum_ggsw, size_evk_inv;
+  int n_coord, coord_len[8], coord_digits[8][8], n_ggsw, n_glwe;
+};
+
+extern "C" void fheram_params_default(fheram_params* p) {  // src/parameters.rs:11-21
+  memset(p, 0, sizeof(*p));
+  p->log_n = 12; p->base2k = 17; p->k_pt = 3; p->k_ct = 51; p->k_addr = 68;
+  p->k_evk_trace = 68; p->k_evk_ggsw_inv = 85; p->word_size = 4; p->n_decomp = 4;
+  for (int i = 0; i < 4; i++) p->decomp_n[i] = 3;
+  p->max_addr = 1u << 14;
+}
+extern "C" void fheram_params_readme(fheram_params* p) {  // README.md:17-34
+  fheram_params_default(p);
+  p->k_pt = 9;
+  p->max_addr = 1u << 18;
+}
+
+// get_base_2d, src/base.rs:84-108
+static int base2d(uint32_t value, const int32_t* base, int n_base, int32_t* lens, int32_t* digits) {
+  int n_out = 0;
+  uint32_t vm1 = value - 1;
+  int bits = vm1 == 0 ? 0 : 32 - __builtin_clz(vm1);
+  while (bits != 0 && n_out < 8) {
+    int len = 0;
+    for (int i = 0; i < n_base; i++) {
+      int b = base[i];
+      if (b <= bits) { digits[n_out * 8 + len++] = b; bits -= b; }
+      else { if (bits != 0) { digits[n_out * 8 + len++] = bits; bits = 0; } break; }
+    }
+    lens[n_out++] = len;
+  }
+  return n_out;
+}
+
+static Derived derive(const fheram_params* p) {
+  Derived d;
+  memset(&d, 0, sizeof(d));
+  d.log_n = p->log_n; d.n = 1 << p->log_n;
+  d.size_ct = cdiv(p->k_ct, p->base2k);
+  d.dnum_ct = d.size_ct;                       // src/parameters.rs:138-140
+  d.size_addr = cdiv(p->k_addr, p->base2k);
+  d.size_evk_trace = cdiv(p->k_evk_trace, p->base2k);
+  d.dnum_ggsw = cdiv(p->k_addr, p->base2k);    // src/parameters.rs:142-144
+  d.size_evk_inv = cdiv(p->k_evk_ggsw_inv, p->base2k);
+  int32_t lens[8], digits[64];
+  d.n_coord = base2d((uint32_t)p->max_addr, p->decomp_n, p->n_decomp, lens, digits);
+  for (int i = 0; i < d.n_coord; i++) {
+    d.coord_len[i] = lens[i];
+    for (int j = 0; j < lens[i]; j++) d.coord_digits[i][j] = digits[i * 8 + j];
+    d.n_ggsw += lens[i];
+  }
+  d.n_glwe = (int)((p->max_addr + (uint64_t)d.n - 1) / (uint64_t)d.n);
+  return d;
+}
+
+extern "C" size_t fheram_glwe_len(const fheram_params* p) { Derived d = derive(p); return (size_t)2 * d.size_ct * d.n; }
+extern "C" size_t fheram_ggsw_len(const fheram_params* p) { Derived d = derive(p); return (size_t)d.dnum_ct * 4 * d.size_addr * d.n; }
+extern "C" size_t fheram_atk_len(const fheram_params* p) { Derived d = derive(p); return (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n; }
+extern "C" size_t fheram_evk_inv_len(const fheram_params* p) { Derived d = derive(p); return (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n; }
+extern "C" int fheram_n_trace_keys(const fheram_params* p) { return p->log_n; }
+extern "C" int fheram_n_ggsw(const fheram_params* p) { return derive(p).n_ggsw; }
+extern "C" int fheram_n_glwe_per_subram(const fheram_params* p) { return derive(p).n_glwe; }
+extern "C" int fheram_base2d(const fheram_params* p, int32_t lens[8], int32_t digits[64]) {
+  return base2d((uint32_t)p->max_addr, p->decomp_n, p->n_decomp, lens, digits);
+}
+static int64_t galois(int log_n, int i) {  // Poulpy GLWE::trace_galois_elements
+  if (i == 0) return -1;
+  const uint64_t two_n = 2ull << log_n;
+  uint64_t r = 1, b = 5, e = 1ull << (i - 1);
+  while (e) { if (e & 1) r = r * b % two_n; b = b * b % two_n; e >>= 1; }
+  return (int64_t)r;
+}
+extern "C" int64_t fheram_trace_galois_element(const fheram_params* p, int i) { return galois(p->log_n, i); }
+
+static uint32_t revbits(uint32_t x, int n) {  // src/lib.rs:23-26
+  uint32_t r = 0;
+  for (int i = 0; i < n; i++) r |= ((x >> i) & 1u) << (n - 1 - i);
+  return r;
+}
+static int ilog2(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
+
+// --------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return fail(FHERAM_ERR_CUDA, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+    bytes = need;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct fheram_ctx {
+  fheram_params params;
+  Derived d;
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  double2* d_tw = nullptr;  // tw6 | tw7c | tw8c | tw9 | tw10c
+  Twiddles tw;
+  int* d_err = nullptr;
+  uint64_t launches = 0;
+  DevBuf stage64;   // int64 staging for uploads / downloads
+  DevBuf scratch;   // per-CTA scratch of the vmp kernels
+  DevBuf opbuf[3];  // op-level entry points
+  long ct_stride() const { return (long)2 * d.size_ct * d.n; }          // ints per GLWE(k_ct)
+  long ggsw_raw_len() const { return (long)d.dnum_ct * 4 * d.size_addr * d.n; }
+  long ggsw_prep_len() const { return (long)d.dnum_ct * 2 * 2 * d.size_addr * kM; }  // double2
+  long atk_prep_len() const { return (long)d.dnum_ct * 2 * d.size_evk_trace * kM; }
+  long evk_inv_prep_len() const { return (long)d.dnum_ggsw * 2 * d.size_evk_inv * kM; }
+};
+
+static size_t smem_bytes(int R, int CIN, bool xsmem) {
+  return (size_t)R * CIN * kM * sizeof(double2) + kM * sizeof(double2) +
+         (xsmem ? (size_t)2 * R * kN * sizeof(int) : 0);
+}
+
+// kernel instantiations used by the schedules
+#define K_EXT      k_vmp<3, 2, 4, 3, MODE_EXT, false>
+#define K_TRACE    k_vmp<3, 1, 4, 3, MODE_TRACE, true>
+#define K_COMBINE2 k_vmp<3, 1, 4, 3, MODE_COMBINE2, true>
+#define K_AUTO3    k_vmp<3, 1, 4, 3, MODE_AUTO, false>
+#define K_AUTO_INV k_vmp<4, 1, 5, 4, MODE_AUTO, false>
+#define K_EXPAND   k_vmp<4, 1, 5, 4, MODE_EXPAND, false>
+
+static int set_attrs() {
+  CU(cudaFuncSetAttribute(K_EXT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 2, false)));
+  CU(cudaFuncSetAttribute(K_TRACE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
+  CU(cudaFuncSetAttribute(K_COMBINE2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
+  CU(cudaFuncSetAttribute(K_AUTO3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, false)));
+  CU(cudaFuncSetAttribute(K_AUTO_INV, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
+  CU(cudaFuncSetAttribute(K_EXPAND, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
+  return 0;
+}
+
+static void zeta(int s, int b, double2* out) {
+  const long double PI = 3.14159265358979323846264338327950288L;
+  long double th = (0.25L + (long double)revbits((uint32_t)b, s)) / (long double)(1ull << s);
+  out->x = (double)cosl(PI * th);
+  out->y = (double)sinl(PI * th);
+}
+
+extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx** out) {
+  if (!p || !out) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (p->log_n != 12 || p->base2k != 17 || p->k_ct != 51 || p->k_addr != 68 ||
+      p->k_evk_trace != 68 || p->k_evk_ggsw_inv != 85)
+    return fail(FHERAM_ERR_INVALID,
+                "unsupported cryptographic parameters: kernels are built for log_n=12 base2k=17 "
+                "k_ct=51 k_addr=68 k_evk_trace=68 k_evk_ggsw_inv=85 (src/parameters.rs:11-18)");
+  if (p->word_size < 1 || p->word_size > 16 || p->max_addr < 1 || p->k_pt < 1 || p->k_pt > 16)
+    return fail(FHERAM_ERR_INVALID, "bad word_size / max_addr / k_pt");
+  {
+    int s = 0;
+    for (int i = 0; i < p->n_decomp; i++) s += p->decomp_n[i];
+    if (s != p->log_n) return fail(FHERAM_ERR_INVALID, "sum(decomp_n) != log_n (src/parameters.rs:168)");
+  }
+  Derived d = derive(p);
+  if (d.n_coord > 2)
+    return fail(FHERAM_ERR_INVALID, "max_addr > N^2: the reference's read loop only supports two coordinates");
+  if (d.n_glwe & (d.n_glwe - 1))
+    return fail(FHERAM_ERR_INVALID, "max_addr / N must be a power of two");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(FHERAM_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(FHERAM_ERR_INVALID, "device %d out of range", device);
+  CU(cudaSetDevice(device));
+  fheram_ctx* c = new fheram_ctx();
+  c->params = *p;
+  c->d = d;
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete c;
+    return fail(FHERAM_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only",
+                prop.name, prop.major, prop.minor);
+  }
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  TRY(set_attrs());
+  // twiddles
+  std::vector<double2> lo(64), hi(64 + 64 + 128 + 512 + 512);
+  lo[0] = make_double2(0, 0);
+  for (int s = 0; s < 6; s++)
+    for (int b = 0; b < (1 << s); b++) zeta(s, b, &lo[(1 << s) + b]);
+  double2* q = hi.data();
+  for (int b = 0; b < 64; b++) zeta(6, b, q++);
+  for (int b = 0; b < 64; b++) zeta(7, 2 * b, q++);
+  for (int b = 0; b < 128; b++) zeta(8, 2 * b, q++);
+  for (int b = 0; b < 512; b++) zeta(9, b, q++);
+  for (int b = 0; b < 512; b++) zeta(10, 2 * b, q++);
+  CU(cudaMemcpyToSymbol(c_tw_lo, lo.data(), sizeof(double2) * 64));
+  CU(cudaMalloc(&c->d_tw, sizeof(double2) * hi.size()));
+  CU(cudaMemcpy(c->d_tw, hi.data(), sizeof(double2) * hi.size(), cudaMemcpyHostToDevice));
+  c->tw.tw6 = c->d_tw;
+  c->tw.tw7c = c->d_tw + 64;
+  c->tw.tw8c = c->d_tw + 128;
+  c->tw.tw9 = c->d_tw + 256;
+  c->tw.tw10c = c->d_tw + 768;
+  CU(cudaMalloc(&c->d_err, sizeof(int)));
+  CU(cudaMemset(c->d_err, 0, sizeof(int)));
+  TRY(c->scratch.ensure((size_t)c->sm_count * 2 * c->ct_stride() * sizeof(int)));
+  *out = c;
+  return 0;
+}
+
+extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->stage64.release(); c->scratch.release();
+  for (auto& b : c->opbuf) b.release();
+  cudaFree(c->d_tw); cudaFree(c->d_err);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+extern "C" int fheram_ctx_synchronize(fheram_ctx* c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" void* fheram_ctx_stream(fheram_ctx* c) { return (void*)c->stream; }
+extern "C" uint64_t fheram_ctx_launch_count(const fheram_ctx* c) { return c->launches; }
+
+// --------------------------------------------------------------------------------------
+// host <-> device limb conversion
+// --------------------------------------------------------------------------------------
+static int upload_i64(fheram_ctx* c, const int64_t* h, size_t n, int* d_out) {
+  const size_t chunk = (size_t)64 << 20;  // limbs per staging pass (512 MiB of int64)
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t m = n - off < chunk ? n - off : chunk;
+    TRY(c->stage64.ensure(m * sizeof(int64_t)));
+    CU(cudaMemcpyAsync(c->stage64.p, h + off, m * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>((const long long*)c->stage64.p, d_out + off, m, c->d_err);
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  int err = 0;
+  CU(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    CU(cudaMemset(c->d_err, 0, sizeof(int)));
+    return fail(FHERAM_ERR_RANGE, "limb outside +-2^30: ciphertext limbs must be (nearly) normalised");
+  }
+  return 0;
+}
+static int download_i64(fheram_ctx* c, const int* d_in, size_t n, int64_t* h) {
+  const size_t chunk = (size_t)64 << 20;
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t m = n - off < chunk ? n - off : chunk;
+    TRY(c->stage64.ensure(m * sizeof(int64_t)));
+    k_i32_to_i64<<<c->sm_count * 8, 256, 0, c->stream>>>(d_in + off, (long long*)c->stage64.p, m);
+    c->launches++;
+    CU(cudaMemcpyAsync(h + off, c->stage64.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+extern "C" int fheram_download_glwe(fheram_ctx* c, const int32_t* d_in, int n_glwe, int64_t* out) {
+  CU(cudaSetDevice(c->device));
+  return download_i64(c, d_in, (size_t)n_glwe * c->ct_stride(), out);
+}
+
+// --------------------------------------------------------------------------------------
+// launches
+// --------------------------------------------------------------------------------------
+static VmpArgs base_args(fheram_ctx* c, int n_items, const int* src, int* dst, long ct_stride) {
+  VmpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_items = n_items;
+  a.src = src; a.dst = dst;
+  a.ct_stride = ct_stride;
+  a.scratch = (int*)c->scratch.p;
+  a.sign = 1;
+  a.tw = c->tw;
+  return a;
+}
+template <typename K>
+static int launch(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem) {
+  if (a.n_items <= 0) return 0;
+  int grid = a.n_items < c->sm_count ? a.n_items : c->sm_count;
+  kernel<<<grid, kThreads, smem, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// vmp_prepare of n_mat matrices
+static int prepare(fheram_ctx* c, const int* raw, long raw_stride, double2* out, long out_stride,
+                   int n_mat, int rows, int cin, int lout) {
+  PrepArgs a;
+  a.raw = raw; a.out = out; a.raw_stride = raw_stride; a.out_stride = out_stride;
+  a.rows = rows; a.cin = cin; a.lout = lout; a.tw = c->tw;
+  int grid = n_mat * rows * cin * 2 * lout;
+  k_prepare<<<grid, kThreads, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// keys
+// --------------------------------------------------------------------------------------
+struct fheram_keys {
+  fheram_ctx* c;
+  double2* atk = nullptr;      // [log_n] prepared trace keys
+  double2* atk_inv = nullptr;  // prepared atk_ggsw_inv
+  double2* tsk = nullptr;      // prepared tsk_ggsw_inv
+};
+
+extern "C" int fheram_keys_prepare(fheram_ctx* c, const int64_t* atk_glwe, const int64_t* tsk,
+                                   const int64_t* atk_inv, fheram_keys** out) {  // src/keys.rs:34-71
+  if (!c || !atk_glwe || !tsk || !atk_inv || !out) return fail(FHERAM_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  fheram_keys* k = new fheram_keys();
+  k->c = c;
+  const size_t atk_raw = (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n;
+  const size_t inv_raw = (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n;
+  int* tmp = nullptr;
+  CU(cudaMalloc(&tmp, sizeof(int) * (atk_raw * d.log_n > inv_raw ? atk_raw * d.log_n : inv_raw)));
+  CU(cudaMalloc(&k->atk, sizeof(double2) * c->atk_prep_len() * d.log_n));
+  CU(cudaMalloc(&k->atk_inv, sizeof(double2) * c->evk_inv_prep_len()));
+  CU(cudaMalloc(&k->tsk, sizeof(double2) * c->evk_inv_prep_len()));
+  TRY(upload_i64(c, atk_glwe, atk_raw * d.log_n, tmp));
+  TRY(prepare(c, tmp, (long)atk_raw, k->atk, c->atk_prep_len(), d.log_n, d.dnum_ct, 1, d.size_evk_trace));
+  CU(cudaStreamSynchronize(c->stream));
+  TRY(upload_i64(c, atk_inv, inv_raw, tmp));
+  TRY(prepare(c, tmp, (long)inv_raw, k->atk_inv, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv));
+  CU(cudaStreamSynchronize(c->stream));
+  TRY(upload_i64(c, tsk, inv_raw, tmp));
+  TRY(prepare(c, tmp, (long)inv_raw, k->tsk, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaFree(tmp));
+  *out = k;
+  return 0;
+}
+extern "C" int fheram_keys_destroy(fheram_keys* k) {
+  if (!k) return 0;
+  cudaSetDevice(k->c->device);
+  cudaFree(k->atk); cudaFree(k->atk_inv); cudaFree(k->tsk);
+  delete k;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// addresses
+// --------------------------------------------------------------------------------------
+struct fheram_address {
+  fheram_ctx* c;
+  int count = 0;
+  int* raw = nullptr;        // [count][n_ggsw] raw GGSW, int32
+  double2* prep = nullptr;   // [count][n_ggsw] prepared GGSW
+  int* inv_raw = nullptr;    // [n_ggsw] GGSW(X^+digit), built lazily by write
+  double2* inv_prep = nullptr;
+  bool inv_ready = false;
+};
+
+extern "C" int fheram_address_load_batch(fheram_ctx* c, const int64_t* ggsw, int n, fheram_address** out) {
+  if (!c || !ggsw || !out || n < 1) return fail(FHERAM_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  fheram_address* a = new fheram_address();
+  a->c = c; a->count = n;
+  const size_t nm = (size_t)n * d.n_ggsw;
+  CU(cudaMalloc(&a->raw, sizeof(int) * nm * c->ggsw_raw_len()));
+  CU(cudaMalloc(&a->prep, sizeof(double2) * nm * c->ggsw_prep_len()));
+  TRY(upload_i64(c, ggsw, nm * c->ggsw_raw_len(), a->raw));
+  // CoordinatePrepared::prepare, src/coordinate_prepared.rs:104-116
+  TRY(prepare(c, a->raw, c->ggsw_raw_len(), a->prep, c->ggsw_prep_len(), (int)nm, d.dnum_ct, 2, d.size_addr));
+  CU(cudaStreamSynchronize(c->stream));
+  *out = a;
+  return 0;
+}
+extern "C" int fheram_address_load(fheram_ctx* c, const int64_t* ggsw, fheram_address** out) {
+  return fheram_address_load_batch(c, ggsw, 1, out);
+}
+extern "C" int fheram_address_count(const fheram_address* a) { return a ? a->count : 0; }
+extern "C" int fheram_address_destroy(fheram_address* a) {
+  if (!a) return 0;
+  cudaSetDevice(a->c->device);
+  cudaFree(a->raw); cudaFree(a->prep); cudaFree(a->inv_raw); cudaFree(a->inv_prep);
+  delete a;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// schedule building blocks (all asynchronous on c->stream, device buffers only)
+// --------------------------------------------------------------------------------------
+// CoordinatePrepared::product[_inplace] (src/coordinate_prepared.rs:147-177): chain of n_dig
+// external products; matrices mats + dig*ggsw_prep_len (+ (item / mat_div) * mat_stride).
+static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* src_map, int src_mod,
+                         int* dst, const double2* mats, int n_dig, int mat_div, long mat_stride) {
+  VmpArgs a = base_args(c, n_items, src, dst, c->ct_stride());
+  a.src_map = src_map; a.src_mod = src_mod;
+  a.n_steps = n_dig;
+  for (int s = 0; s < n_dig; s++) a.mat[s] = mats + (size_t)s * c->ggsw_prep_len();
+  a.mat_div = mat_div; a.mat_stride = mat_stride;
+  return launch(c, K_EXT, a, smem_bytes(3, 2, false));
+}
+// chain of { glwe_rsh(1); automorphism_add with trace key i } for i in [g0, g1)
+// (glwe_trace_inplace, and the one-sided levels of GLWEPacker::combine)
+static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, const int* src,
+                           const int* src_map, int src_mod, int src_div, int* dst, int g0, int g1,
+                           int rot_mod = 0, int rot_mul = 0, int rot_const = 0, int sign = 1) {
+  VmpArgs a = base_args(c, n_items, src, dst, c->ct_stride());
+  a.src_map = src_map; a.src_mod = src_mod; a.src_div = src_div;
+  a.n_steps = g1 - g0;
+  for (int s = 0; s < a.n_steps; s++) {
+    a.mat[s] = k->atk + (size_t)(g0 + s) * c->atk_prep_len();
+    a.gal[s] = (int)((galois(c->d.log_n, g0 + s) + 2 * kN) % (2 * kN));
+  }
+  a.rot_mod = rot_mod; a.rot_mul = rot_mul; a.rot_const = rot_const; a.sign = sign;
+  if (a.n_steps == 0) {
+    // no level to run: only the (feed-order) gather remains
+    if (!src_map) return fail(FHERAM_ERR_INVALID, "empty trace chain");
+    k_gather<<<c->sm_count * 8, 256, 0, c->stream>>>(dst, src, src_map, src_mod, n_items, c->ct_stride());
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
+  return launch(c, K_TRACE, a, smem_bytes(3, 1, true));
+}
+// GLWEPacker::combine, both operands present, at tree level `level` (0-based absolute):
+// in[2i], in[2i+1] -> out[i]
+static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const int* in, int* out, int level) {
+  VmpArgs a = base_args(c, n_items, in, out, c->ct_stride());
+  a.n_steps = 1;
+  a.mat[0] = k->atk + (size_t)level * c->atk_prep_len();
+  a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
+  a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true));
+}
+
+// GLWEPacker over `width` inputs per group (width a power of two), feed order = index order
+// of `buf` (caller wrote inputs at m = bitrev(h)).  One-sided levels [0, log_n - log2(width_total))
+// must already be applied.  Runs two-sided levels first_level .. first_level + log2(width) - 1,
+// ping-ponging between buf and tmp; returns the buffer holding the [groups] results.
+static int run_pack_levels(fheram_ctx* c, const fheram_keys* k, int groups, int width, int first_level,
+                           int* buf, int* tmp, int** result) {
+  int* in = buf;
+  int* out = tmp;
+  int level = first_level;
+  for (int wdt = width; wdt > 1; wdt >>= 1, level++) {
+    TRY(run_combine2(c, k, groups * (wdt / 2), in, out, level));
+    int* t = in; in = out; out = t;
+  }
+  *result = in;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// RAM
+// --------------------------------------------------------------------------------------
+struct fheram_ram {
+  fheram_ctx* c;
+  int shard = 0, n_shards = 1;
+  int n_local = 0;           // local polynomials per sub-RAM
+  int* data = nullptr;       // [word_size][n_local] GLWE   (SubRam::data, src/ram.rs:299)
+  int* tree = nullptr;       // [word_size] GLWE            (SubRam::tree[0][0], src/ram.rs:300)
+  bool state = false;        // src/ram.rs:302
+  bool loaded = false;
+  int* feed_map = nullptr;   // device: [word_size*n_local] feed position -> data index
+  DevBuf bufA, bufB;         // work arenas [B][word_size][n_local] GLWE
+  DevBuf partial;            // [B][word_size] packed partials
+  DevBuf result;             // [B][word_size] results
+  DevBuf wbuf;               // uploaded write words
+  DevBuf all;                // results of a chunked batched read
+};
+
+static int ram_create(fheram_ctx* c, int shard, int n_shards, fheram_ram** out) {
+  if (!c || !out) return fail(FHERAM_ERR_INVALID, "null argument");
+  const Derived& d = c->d;
+  if (n_shards < 1 || (n_shards & (n_shards - 1)) || n_shards > d.n_glwe || shard < 0 || shard >= n_shards)
+    return fail(FHERAM_ERR_INVALID, "n_shards must be a power of two <= max_addr/N and 0 <= shard < n_shards");
+  CU(cudaSetDevice(c->device));
+  fheram_ram* r = new fheram_ram();
+  r->c = c; r->shard = shard; r->n_shards = n_shards;
+  r->n_local = d.n_glwe / n_shards;
+  const int ws = c->params.word_size;
+  CU(cudaMalloc(&r->data, sizeof(int) * (size_t)ws * r->n_local * c->ct_stride()));
+  CU(cudaMalloc(&r->tree, sizeof(int) * (size_t)ws * c->ct_stride()));
+  CU(cudaMemset(r->tree, 0, sizeof(int) * (size_t)ws * c->ct_stride()));
+  // feed order of the packer (src/ram.rs:425-435): position m of the local tree reads local
+  // polynomial h' = bitrev(m)
+  std::vector<int> map((size_t)ws * r->n_local);
+  const int lg = ilog2(r->n_local);
+  for (int s = 0; s < ws; s++)
+    for (int m = 0; m < r->n_local; m++) map[(size_t)s * r->n_local + m] = s * r->n_local + (int)revbits(m, lg);
+  CU(cudaMalloc(&r->feed_map, sizeof(int) * map.size()));
+  CU(cudaMemcpy(r->feed_map, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice));
+  *out = r;
+  return 0;
+}
+extern "C" int fheram_ram_create(fheram_ctx* c, fheram_ram** out) { return ram_create(c, 0, 1, out); }
+extern "C" int fheram_ram_create_sharded(fheram_ctx* c, int shard, int n_shards, fheram_ram** out) {
+  return ram_create(c, shard, n_shards, out);
+}
+extern "C" int fheram_ram_destroy(fheram_ram* r) {
+  if (!r) return 0;
+  cudaSetDevice(r->c->device);
+  cudaFree(r->data); cudaFree(r->tree); cudaFree(r->feed_map);
+  r->bufA.release(); r->bufB.release(); r->partial.release(); r->result.release(); r->wbuf.release(); r->all.release();
+  delete r;
+  return 0;
+}
+// cts: the FULL RAM [word_size][n_glwe]; a sharded RAM keeps h = shard + n_shards*h'
+extern "C" int fheram_ram_load(fheram_ram* r, const int64_t* cts) {
+  if (!r || !cts) return fail(FHERAM_ERR_INVALID, "null argument");
+  fheram_ctx* c = r->c;
+  CU(cudaSetDevice(c->device));
+  const int ws = c->params.word_size, G = c->d.n_glwe;
+  const size_t L = (size_t)c->ct_stride();
+  if (r->n_shards == 1) {
+    TRY(upload_i64(c, cts, (size_t)ws * G * L, r->data));
+  } else {
+    for (int s = 0; s < ws; s++)
+      for (int hp = 0; hp < r->n_local; hp++) {
+        const int h = r->shard + r->n_shards * hp;
+        TRY(upload_i64(c, cts + ((size_t)s * G + h) * L, L, r->data + ((size_t)s * r->n_local + hp) * L));
+      }
+  }
+  r->loaded = true;
+  r->state = false;
+  return 0;
+}
+extern "C" int fheram_ram_store(fheram_ram* r, int64_t* cts) {
+  if (!r || !cts) return fail(FHERAM_ERR_INVALID, "null argument");
+  fheram_ctx* c = r->c;
+  CU(cudaSetDevice(c->device));
+  const int ws = c->params.word_size, G = c->d.n_glwe;
+  const size_t L = (size_t)c->ct_stride();
+  if (r->n_shards == 1) return download_i64(c, r->data, (size_t)ws * G * L, cts);
+  for (int s = 0; s < ws; s++)
+    for (int hp = 0; hp < r->n_local; hp++) {
+      const int h = r->shard + r->n_shards * hp;
+      TRY(download_i64(c, r->data + ((size_t)s * r->n_local + hp) * L, L, cts + ((size_t)s * G + h) * L));
+    }
+  return 0;
+}
+extern "C" int fheram_ram_tree_store(fheram_ram* r, int64_t* cts) {
+  if (!r || !cts) return fail(FHERAM_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(r->c->device));
+  return download_i64(r->c, r->tree, (size_t)r->c->params.word_size * r->c->ct_stride(), cts);
+}
+extern "C" int fheram_ram_state(const fheram_ram* r) { return r && r->state ? 1 : 0; }
+
+static int first_coord_ggsw(const Derived& d, int coord) {
+  int f = 0;
+  for (int i = 0; i < coord; i++) f += d.coord_len[i];
+  return f;
+}
+
+// Local stage of SubRam::read / read_prepare_write for B addresses (src/ram.rs:411-449 /
+// 487-528): rotate every local polynomial by the first coordinate and pack coefficient 0 of
+// each into one partial ciphertext per (address, sub-RAM).  inplace = read_prepare_write
+// (the rotated polynomials overwrite SubRam::data, src/ram.rs:502-504; B must be 1).
+// Result: r->partial = [B][word_size] GLWE.
+static int ram_local_stage(fheram_ram* r, const fheram_address* addr, int first_addr, int B,
+                           const fheram_keys* k, bool inplace) {
+  fheram_ctx* c = r->c;
+  const Derived& d = c->d;
+  const int ws = c->params.word_size, nl = r->n_local;
+  const long L = c->ct_stride();
+  const int per_addr = ws * nl;
+  const int items = B * per_addr;
+  TRY(r->bufA.ensure(sizeof(int) * (size_t)items * L));
+  TRY(r->bufB.ensure(sizeof(int) * (size_t)items * L));
+  TRY(r->partial.ensure(sizeof(int) * (size_t)B * ws * L));
+  int* A = (int*)r->bufA.p;
+  int* Bb = (int*)r->bufB.p;
+  const double2* mats = addr->prep + (size_t)first_addr * d.n_ggsw * c->ggsw_prep_len();
+  const long mat_stride = (long)d.n_ggsw * c->ggsw_prep_len();
+  const int lg_total = ilog2(d.n_glwe);          // two-sided levels of the full tree
+  const int one_sided = d.log_n - lg_total;      // levels with a single non-empty child
+  if (d.n_coord == 1) {
+    // max_addr <= N: product on data[0] only (src/ram.rs:450-452); "partial" = rotated poly
+    if (inplace) {
+      TRY(run_ext_chain(c, per_addr, r->data, nullptr, 0, r->data, mats, d.coord_len[0], 0, 0));
+      CU(cudaMemcpyAsync(r->partial.p, r->data, sizeof(int) * (size_t)ws * L, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      TRY(run_ext_chain(c, items, r->data, nullptr, per_addr, (int*)r->partial.p, mats, d.coord_len[0], per_addr, mat_stride));
+    }
+    return 0;
+  }
+  if (inplace) {
+    // src/ram.rs:502-504 product_inplace on every polynomial, then pack (src/ram.rs:510-521)
+    TRY(run_ext_chain(c, per_addr, r->data, nullptr, 0, r->data, mats, d.coord_len[0], 0, 0));
+    TRY(run_trace_chain(c, k, per_addr, r->data, r->feed_map, per_addr, 0, A, 0, one_sided));
+  } else {
+    // src/ram.rs:429-435: product into tmp_ct then packer.add, in feed order
+    TRY(run_ext_chain(c, items, r->data, r->feed_map, per_addr, A, mats, d.coord_len[0], per_addr, mat_stride));
+    TRY(run_trace_chain(c, k, items, A, nullptr, 0, 0, A, 0, one_sided));
+  }
+  int* res = nullptr;
+  TRY(run_pack_levels(c, k, B * ws, nl, one_sided, A, Bb, &res));
+  CU(cudaMemcpyAsync(r->partial.p, res, sizeof(int) * (size_t)B * ws * L, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+// Finishing stage for reads [first, first+count) of a batch of n_total: combine the
+// n_shards partials of each (read, sub-RAM) through the top packer levels, rotate by the
+// second coordinate (src/ram.rs:453-455) and trace (src/ram.rs:457).  gathered =
+// [n_shards][n_total][word_size] GLWE (rank-major).  store_tree: read_prepare_write keeps the
+// rotated packed polynomial in SubRam::tree[0][0] (src/ram.rs:525-527,499-504).
+static int ram_finish_stage(fheram_ram* r, const int* gathered, int n_total, int first, int count,
+                            const fheram_address* addr, int first_addr, const fheram_keys* k,
+                            bool store_tree) {
+  fheram_ctx* c = r->c;
+  const Derived& d = c->d;
+  const int ws = c->params.word_size, S = r->n_shards;
+  const long L = c->ct_stride();
+  TRY(r->result.ensure(sizeof(int) * (size_t)count * ws * L));
+  int* res = (int*)r->result.p;
+  const int groups = count * ws;
+  const int* packed = nullptr;
+  if (d.n_coord == 1) {
+    packed = gathered + (size_t)first * ws * L;
+    if (store_tree) {
+      // n2 == 1: result = copy of data[0] (src/ram.rs:536-538); no tree
+      CU(cudaMemcpyAsync(res, packed, sizeof(int) * (size_t)groups * L, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      CU(cudaMemcpyAsync(res, packed, sizeof(int) * (size_t)groups * L, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    TRY(run_trace_chain(c, k, groups, res, nullptr, 0, 0, res, 0, d.log_n));
+    return 0;
+  }
+  if (S > 1) {
+    // gather the S partials of each group in tree order: block index bitrev(shard)
+    TRY(r->bufA.ensure(sizeof(int) * (size_t)groups * S * L));
+    TRY(r->bufB.ensure(sizeof(int) * (size_t)groups * S * L));
+    int* A = (int*)r->bufA.p;
+    const int lgS = ilog2(S);
+    for (int blk = 0; blk < S; blk++) {
+      const int shard = (int)revbits(blk, lgS);
+      // A[(g*S + blk)] = gathered[shard][first*ws + g]
+      CU(cudaMemcpy2DAsync(A + (size_t)blk * L, sizeof(int) * (size_t)S * L,
+                           gathered + ((size_t)shard * n_total + first) * ws * L, sizeof(int) * L,
+                           sizeof(int) * L, groups, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    int* out = nullptr;
+    const int first_level = d.log_n - lgS;
+    TRY(run_pack_levels(c, k, groups, S, first_level, A, (int*)r->bufB.p, &out));
+    packed = out;
+  } else {
+    packed = gathered + (size_t)first * ws * L;
+  }
+  const int c1 = first_coord_ggsw(d, 1);
+  const double2* mats = addr->prep + ((size_t)(first_addr + first) * d.n_ggsw + c1) * c->ggsw_prep_len();
+  const long mat_stride = (long)d.n_ggsw * c->ggsw_prep_len();
+  if (store_tree) {
+    TRY(run_ext_chain(c, groups, packed, nullptr, 0, r->tree, mats, d.coord_len[1], ws, mat_stride));
+    CU(cudaMemcpyAsync(res, r->tree, sizeof(int) * (size_t)groups * L, cudaMemcpyDeviceToDevice, c->stream));  // src/ram.rs:535
+  } else {
+    TRY(run_ext_chain(c, groups, packed, nullptr, 0, res, mats, d.coord_len[1], ws, mat_stride));
+  }
+  TRY(run_trace_chain(c, k, groups, res, nullptr, 0, 0, res, 0, d.log_n));  // src/ram.rs:457,540
+  return 0;
+}
+
+static int check_read_args(fheram_ram* r, const fheram_address* addr, const fheram_keys* k) {
+  if (!r || !addr || !k) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (addr->c != r->c || k->c != r->c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
+  if (!r->loaded) return fail(FHERAM_ERR_UNINIT, "unitialized memory: self.data.len()=0 (src/ram.rs:182-185)");
+  if (r->state)
+    return fail(FHERAM_ERR_STATE, "invalid call to Memory.read: internal state is true -> requires calling Memory.write (src/ram.rs:393-396)");
+  return 0;
+}
+
+// reads per chunk of a batched read: bounds the work arenas (chunk * word_size * n_glwe GLWE)
+static int batch_chunk(const fheram_ram* r) {
+  const size_t per_read = (size_t)r->c->params.word_size * r->n_local * r->c->ct_stride() * sizeof(int);
+  size_t budget = (size_t)3 << 30;  // bytes per arena
+  int ch = (int)(budget / (per_read ? per_read : 1));
+  if (ch < 1) ch = 1;
+  if (ch > 64) ch = 64;
+  return ch;
+}
+
+extern "C" int fheram_ram_read_batch_device(fheram_ram* r, const fheram_address* addr,
+                                            const fheram_keys* k, const int32_t** d_out) {
+  TRY(check_read_args(r, addr, k));
+  if (r->n_shards != 1) return fail(FHERAM_ERR_INVALID, "sharded RAM: use read_local_device / read_finish_device");
+  fheram_ctx* c = r->c;
+  CU(cudaSetDevice(c->device));
+  const int B = addr->count, ws = c->params.word_size;
+  const long L = c->ct_stride();
+  const int chunk = batch_chunk(r);
+  DevBuf& all = r->all;  // results of every chunk
+  if (B <= chunk) {
+    TRY(ram_local_stage(r, addr, 0, B, k, false));
+    TRY(ram_finish_stage(r, (const int*)r->partial.p, B, 0, B, addr, 0, k, false));
+    *d_out = (const int32_t*)r->result.p;
+    return 0;
+  }
+  TRY(all.ensure(sizeof(int) * (size_t)B * ws * L));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    TRY(ram_local_stage(r, addr, b0, nb, k, false));
+    TRY(ram_finish_stage(r, (const int*)r->partial.p, nb, 0, nb, addr, b0, k, false));
+    CU(cudaMemcpyAsync((int*)all.p + (size_t)b0 * ws * L, r->result.p, sizeof(int) * (size_t)nb * ws * L,
+                       cudaMemcpyDeviceToDevice, c->stream));
+  }
+  *d_out = (const int32_t*)all.p;
+  return 0;
+}
+
+extern "C" int fheram_ram_read_batch(fheram_ram* r, const fheram_address* addr, const fheram_keys* k, int64_t* out) {
+  if (!out) return fail(FHERAM_ERR_INVALID, "null argument");
+  const int32_t* d = nullptr;
+  TRY(fheram_ram_read_batch_device(r, addr, k, &d));
+  return download_i64(r->c, d, (size_t)addr->count * r->c->params.word_size * r->c->ct_stride(), out);
+}
+extern "C" int fheram_ram_read(fheram_ram* r, const fheram_address* addr, const fheram_keys* k, int64_t* out) {
+  if (addr && addr->count != 1) return fail(FHERAM_ERR_INVALID, "fheram_ram_read takes a single address");
+  return fheram_ram_read_batch(r, addr, k, out);
+}
+
+extern "C" int fheram_ram_read_local_device(fheram_ram* r, const fheram_address* addr,
+                                            const fheram_keys* k, const int32_t** d_partial) {
+  TRY(check_read_args(r, addr, k));
+  CU(cudaSetDevice(r->c->device));
+  TRY(ram_local_stage(r, addr, 0, addr->count, k, false));
+  *d_partial = (const int32_t*)r->partial.p;
+  return 0;
+}
+extern "C" int fheram_ram_read_finish_device(fheram_ram* r, const int32_t* d_gathered, int n_total,
+                                             int first, int count, const fheram_address* addr,
+                                             const fheram_keys* k, const int32_t** d_out) {
+  if (!r || !d_gathered || !addr || !k || !d_out) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (first < 0 || count < 0 || first + count > n_total || n_total != addr->count)
+    return fail(FHERAM_ERR_INVALID, "bad read range");
+  CU(cudaSetDevice(r->c->device));
+  TRY(ram_finish_stage(r, d_gathered, n_total, first, count, addr, 0, k, false));
+  *d_out = (const int32_t*)r->result.p;
+  return 0;
+}
+
+// Ram::read_prepare_write (src/ram.rs:196-222, 461-542).  For a sharded RAM the caller runs
+// fheram_ram_rpw_local_device, all-gathers the partials and calls fheram_ram_rpw_finish_device
+// on every rank (the finishing stage is replicated so every rank holds tree[0][0]).
+extern "C" int fheram_ram_rpw_local_device(fheram_ram* r, const fheram_address* addr,
+                                           const fheram_keys* k, const int32_t** d_partial) {
+  TRY(check_read_args(r, addr, k));
+  if (addr->count != 1) return fail(FHERAM_ERR_INVALID, "read_prepare_write takes a single address");
+  CU(cudaSetDevice(r->c->device));
+  TRY(ram_local_stage(r, addr, 0, 1, k, true));
+  *d_partial = (const int32_t*)r->partial.p;
+  return 0;
+}
+extern "C" int fheram_ram_rpw_finish_device(fheram_ram* r, const int32_t* d_gathered,
+                                            const fheram_address* addr, const fheram_keys* k,
+                                            const int32_t** d_out) {
+  if (!r || !d_gathered || !addr || !k || !d_out) return fail(FHERAM_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(r->c->device));
+  TRY(ram_finish_stage(r, d_gathered, 1, 0, 1, addr, 0, k, true));
+  r->state = true;  // src/ram.rs:533
+  *d_out = (const int32_t*)r->result.p;
+  return 0;
+}
+extern "C" int fheram_ram_read_prepare_write(fheram_ram* r, const fheram_address* addr,
+                                             const fheram_keys* k, int64_t* out) {
+  if (!out) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (r && r->n_shards != 1) return fail(FHERAM_ERR_INVALID, "sharded RAM: use rpw_local_device / rpw_finish_device");
+  const int32_t *part = nullptr, *res = nullptr;
+  TRY(fheram_ram_rpw_local_device(r, addr, k, &part));
+  TRY(fheram_ram_rpw_finish_device(r, part, addr, k, &res));
+  return download_i64(r->c, res, (size_t)r->c->params.word_size * r->c->ct_stride(), out);
+}
+
+// CoordinatePrepared::prepare_inv for every coordinate of the address (src/ram.rs:260-271,
+// 278-289 -> src/coordinate_prepared.rs:121-142): GGSW::automorphism(p = -1) of each digit
+// (key-switch-automorphism of the column-0 GLWE of every row with atk_ggsw_inv, column 1 rebuilt
+// with tsk_ggsw_inv) followed by vmp_prepare.
+static int ggsw_invert_device(fheram_ctx* c, const fheram_keys* k, const int* raw, int n_ggsw, int* inv_raw) {
+  const Derived& d = c->d;
+  const long glwe4 = (long)2 * d.size_addr * d.n;  // one GLWE(k_addr), ints
+  const int items = n_ggsw * d.dnum_ct;            // rows
+  {
+    VmpArgs a = base_args(c, items, raw, inv_raw, 2 * glwe4);
+    a.n_steps = 1;
+    a.mat[0] = k->atk_inv;
+    a.gal[0] = 2 * kN - 1;
+    TRY(launch(c, K_AUTO_INV, a, smem_bytes(4, 1, false)));
+  }
+  {
+    VmpArgs a = base_args(c, items, inv_raw, inv_raw + glwe4, 2 * glwe4);
+    a.n_steps = 1;
+    a.mat[0] = k->tsk;
+    a.gal[0] = 1;
+    TRY(launch(c, K_EXPAND, a, smem_bytes(4, 1, false)));
+  }
+  return 0;
+}
+static int address_prepare_inv(fheram_address* a, const fheram_keys* k) {
+  fheram_ctx* c = a->c;
+  const Derived& d = c->d;
+  if (a->count != 1) return fail(FHERAM_ERR_INVALID, "write takes a single address");
+  if (!a->inv_raw) {
+    CU(cudaMalloc(&a->inv_raw, sizeof(int) * (size_t)d.n_ggsw * c->ggsw_raw_len()));
+    CU(cudaMalloc(&a->inv_prep, sizeof(double2) * (size_t)d.n_ggsw * c->ggsw_prep_len()));
+  }
+  TRY(ggsw_invert_device(c, k, a->raw, d.n_ggsw, a->inv_raw));
+  TRY(prepare(c, a->inv_raw, c->ggsw_raw_len(), a->inv_prep, c->ggsw_prep_len(), d.n_ggsw, d.dnum_ct, 2, d.size_addr));
+  a->inv_ready = true;
+  return 0;
+}
+
+// Ram::write (src/ram.rs:226-294).  Works on sharded RAMs without communication: the steps that
+// touch tree[0][0] are replicated on every rank, the rest touches only local polynomials.
+extern "C" int fheram_ram_write(fheram_ram* r, const int64_t* w, const fheram_address* addr_c,
+                                const fheram_keys* k) {
+  if (!r || !w || !addr_c || !k) return fail(FHERAM_ERR_INVALID, "null argument");
+  fheram_address* addr = const_cast<fheram_address*>(addr_c);
+  fheram_ctx* c = r->c;
+  if (addr->c != c || k->c != c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
+  if (!r->state)
+    return fail(FHERAM_ERR_NOT_READY, "invalid call to Memory.write: internal state is false -> requires calling Memory.read_prepare_write (src/ram.rs:555-558)");
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  const int ws = c->params.word_size, nl = r->n_local;
+  const long L = c->ct_stride();
+  const int per = ws * nl;
+  TRY(r->wbuf.ensure(sizeof(int) * (size_t)ws * L));
+  TRY(upload_i64(c, w, (size_t)ws * L, (int*)r->wbuf.p));
+  TRY(r->bufA.ensure(sizeof(int) * (size_t)per * L));
+  TRY(r->bufB.ensure(sizeof(int) * (size_t)per * L));
+  int* A = (int*)r->bufA.p;
+  int* Bb = (int*)r->bufB.p;
+  // GGSW(X^-digit) -> GGSW(X^+digit) for all digits of the address (src/ram.rs:265-271,283-289)
+  TRY(address_prepare_inv(addr, k));
+  // write_first_step (src/ram.rs:544-577): to = to - TRACE(to) + w, normalised
+  int* to = d.n_coord != 1 ? r->tree : r->data;  // n2 == 1: data[0] of every sub-RAM
+  if (d.n_coord == 1) {
+    // data holds one polynomial per sub-RAM (n_local == 1)
+    TRY(run_trace_chain(c, k, ws, r->data, nullptr, 0, 0, A, 0, d.log_n));
+    k_sub_add_normalize<<<c->sm_count * 4, 256, 0, c->stream>>>(to, A, (const int*)r->wbuf.p, 0, ws, L);
+    c->launches++;
+  } else {
+    TRY(run_trace_chain(c, k, ws, r->tree, nullptr, 0, 0, A, 0, d.log_n));
+    k_sub_add_normalize<<<c->sm_count * 4, 256, 0, c->stream>>>(to, A, (const int*)r->wbuf.p, 0, ws, L);
+    c->launches++;
+    // write_mid_step (src/ram.rs:579-632), i = 0
+    const int c1 = first_coord_ggsw(d, 1);
+    const double2* inv1 = addr->inv_prep + (size_t)c1 * c->ggsw_prep_len();
+    TRY(run_ext_chain(c, ws, r->tree, nullptr, 0, r->tree, inv1, d.coord_len[1], 0, 0));  // :610
+    // T1[h] = TRACE(data[h]) (:616);  T2[h] = TRACE(ct_lo * X^-h) (:621,629), h = shard + S*h'
+    TRY(run_trace_chain(c, k, per, r->data, nullptr, 0, 0, A, 0, d.log_n));
+    TRY(run_trace_chain(c, k, per, r->tree, nullptr, 0, nl, Bb, 0, d.log_n, nl,
+                        2 * kN - r->n_shards, (2 * kN - r->shard) % (2 * kN)));
+    // data[h] = normalize(data[h] - T1[h] + T2[h])  (:617,625,626)
+    k_sub_add_normalize<<<c->sm_count * 8, 256, 0, c->stream>>>(r->data, A, Bb, 0, per, L);
+    c->launches++;
+    // the reference leaves ct_lo rotated by X^-1 once per polynomial of the chunk (:629)
+    k_rotate<<<c->sm_count, 256, 0, c->stream>>>(A, r->tree, (2 * kN - (d.n_glwe % (2 * kN))) % (2 * kN), ws, L);
+    c->launches++;
+    CU(cudaMemcpyAsync(r->tree, A, sizeof(int) * (size_t)ws * L, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  // write_last_step (src/ram.rs:634-649): rotate every polynomial back by the first coordinate
+  TRY(run_ext_chain(c, per, r->data, nullptr, 0, r->data, addr->inv_prep, d.coord_len[0], 0, 0));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  r->state = false;  // src/ram.rs:648
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// op-level entry points
+// --------------------------------------------------------------------------------------
+extern "C" int fheram_coordinate_product(fheram_ctx* c, const int64_t* in, int n, const int64_t* ggsws,
+                                         int n_ggsw, int64_t* out) {
+  if (!c || !in || !ggsws || !out || n < 1 || n_ggsw < 1 || n_ggsw > kMaxSteps)
+    return fail(FHERAM_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const long L = c->ct_stride();
+  TRY(c->opbuf[0].ensure(sizeof(int) * (size_t)n * L));
+  TRY(c->opbuf[1].ensure(sizeof(int) * (size_t)n_ggsw * c->ggsw_raw_len()));
+  TRY(c->opbuf[2].ensure(sizeof(double2) * (size_t)n_ggsw * c->ggsw_prep_len()));
+  TRY(upload_i64(c, in, (size_t)n * L, (int*)c->opbuf[0].p));
+  TRY(upload_i64(c, ggsws, (size_t)n_ggsw * c->ggsw_raw_len(), (int*)c->opbuf[1].p));
+  TRY(prepare(c, (int*)c->opbuf[1].p, c->ggsw_raw_len(), (double2*)c->opbuf[2].p, c->ggsw_prep_len(),
+              n_ggsw, c->d.dnum_ct, 2, c->d.size_addr));
+  TRY(run_ext_chain(c, n, (int*)c->opbuf[0].p, nullptr, 0, (int*)c->opbuf[0].p, (double2*)c->opbuf[2].p,
+                    n_ggsw, 0, 0));
+  return download_i64(c, (int*)c->opbuf[0].p, (size_t)n * L, out);
+}
+extern "C" int fheram_external_product_batch(fheram_ctx* c, const int64_t* in, int n, const int64_t* ggsw,
+                                             int64_t* out) {
+  return fheram_coordinate_product(c, in, n, ggsw, 1, out);
+}
+
+extern "C" int fheram_glwe_trace(fheram_ctx* c, const fheram_keys* k, const int64_t* in, int n, int start,
+                                 int end, int64_t* out) {
+  if (!c || !k || !in || !out || n < 1 || start < 0 || end > c->d.log_n || start > end)
+    return fail(FHERAM_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const long L = c->ct_stride();
+  TRY(c->opbuf[0].ensure(sizeof(int) * (size_t)n * L));
+  TRY(upload_i64(c, in, (size_t)n * L, (int*)c->opbuf[0].p));
+  if (end > start) TRY(run_trace_chain(c, k, n, (int*)c->opbuf[0].p, nullptr, 0, 0, (int*)c->opbuf[0].p, start, end));
+  return download_i64(c, (int*)c->opbuf[0].p, (size_t)n * L, out);
+}
+
+extern "C" int fheram_glwe_pack(fheram_ctx* c, const fheram_keys* k, const int64_t* in, int n, int64_t* out) {
+  if (!c || !k || !in || !out || n < 1 || n > kN || (n & (n - 1))) return fail(FHERAM_ERR_INVALID, "n must be a power of two <= N");
+  CU(cudaSetDevice(c->device));
+  const long L = c->ct_stride();
+  TRY(c->opbuf[0].ensure(sizeof(int) * (size_t)n * L));
+  TRY(c->opbuf[1].ensure(sizeof(int) * (size_t)n * L));
+  TRY(c->opbuf[2].ensure(sizeof(int) * (size_t)n));
+  TRY(upload_i64(c, in, (size_t)n * L, (int*)c->opbuf[1].p));
+  const int lg = ilog2(n);
+  std::vector<int> map(n);
+  for (int m = 0; m < n; m++) map[m] = (int)revbits(m, lg);
+  CU(cudaMemcpyAsync(c->opbuf[2].p, map.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int one_sided = c->d.log_n - lg;
+  int* A = (int*)c->opbuf[0].p;
+  TRY(run_trace_chain(c, k, n, (int*)c->opbuf[1].p, (int*)c->opbuf[2].p, n, 0, A, 0, one_sided));
+  int* res = nullptr;
+  TRY(run_pack_levels(c, k, 1, n, one_sided, A, (int*)c->opbuf[1].p, &res));
+  return download_i64(c, res, (size_t)L, out);
+}
+
+extern "C" int fheram_glwe_automorphism(fheram_ctx* c, const fheram_keys* k, int gal_idx, int mode, int rsh,
+                                        const int64_t* in, int n, int64_t* out) {
+  if (!c || !k || !in || !out || n < 1 || gal_idx < 0 || gal_idx >= c->d.log_n || mode < 0 || mode > 2)
+    return fail(FHERAM_ERR_INVALID, "bad argument");
+  if ((mode == 0) == (rsh != 0)) return fail(FHERAM_ERR_INVALID, "mode 0 runs without rsh, modes 1/2 with rsh=1 (the fused kernels' shapes)");
+  CU(cudaSetDevice(c->device));
+  const long L = c->ct_stride();
+  TRY(c->opbuf[0].ensure(sizeof(int) * (size_t)n * L));
+  TRY(c->opbuf[1].ensure(sizeof(int) * (size_t)n * L));
+  TRY(upload_i64(c, in, (size_t)n * L, (int*)c->opbuf[0].p));
+  int* res = (int*)c->opbuf[0].p;
+  if (mode == 0) {
+    VmpArgs a = base_args(c, n, (int*)c->opbuf[0].p, (int*)c->opbuf[1].p, L);
+    a.n_steps = 1;
+    a.mat[0] = k->atk + (size_t)gal_idx * c->atk_prep_len();
+    a.gal[0] = (int)((galois(c->d.log_n, gal_idx) + 2 * kN) % (2 * kN));
+    TRY(launch(c, K_AUTO3, a, smem_bytes(3, 1, false)));
+    res = (int*)c->opbuf[1].p;
+  } else {
+    TRY(run_trace_chain(c, k, n, res, nullptr, 0, 0, res, gal_idx, gal_idx + 1, 0, 0, 0, mode == 1 ? 1 : -1));
+  }
+  return download_i64(c, res, (size_t)n * L, out);
+}
+
+extern "C" int fheram_ggsw_invert(fheram_ctx* c, const fheram_keys* k, const int64_t* ggsw, int n, int64_t* out) {
+  if (!c || !k || !ggsw || !out || n < 1) return fail(FHERAM_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const size_t len = (size_t)n * c->ggsw_raw_len();
+  TRY(c->opbuf[0].ensure(sizeof(int) * len));
+  TRY(c->opbuf[1].ensure(sizeof(int) * len));
+  TRY(upload_i64(c, ggsw, len, (int*)c->opbuf[0].p));
+  TRY(ggsw_invert_device(c, k, (int*)c->opbuf[0].p, n, (int*)c->opbuf[1].p));
+  return download_i64(c, (int*)c->opbuf[1].p, len, out);
+}

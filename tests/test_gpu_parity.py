@@ -1,0 +1,227 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Bit-exact on every ciphertext limb; decrypt-level acceptance as examples/fhe-ram.rs:104-176."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_glwe(rng, params, n):
+    # normalised base-2^17 limbs, BASELINE.json config 2 distribution
+    return rng.integers(-(1 << 16), 1 << 16, size=(n, params.glwe_len()), dtype=np.int64)
+
+
+def test_external_product_matches_oracle(scenario):
+    from fhe_ram_b200 import api
+    s = scenario()
+    rng = np.random.default_rng(1)
+    n = 5
+    cts = _rand_glwe(rng, s.params, n)
+    addr = s.address(1234)
+    ggsw = addr.data[: s.params.ggsw_len()]
+    got = api.external_product_batch(s.params, cts, ggsw)
+    for i in range(n):
+        want = s.orc.external_product(cts[i], ggsw)
+        assert np.array_equal(got[i], want), f"ct {i}: {np.count_nonzero(got[i] != want)} limbs differ"
+
+
+def test_external_product_adversarial_limbs(scenario):
+    """extreme digits (all -2^16 / 2^16-1) stress the f64 exactness margin."""
+    from fhe_ram_b200 import api
+    s = scenario()
+    p = s.params
+    cts = np.full((2, p.glwe_len()), -(1 << 16), dtype=np.int64)
+    cts[1, :] = (1 << 16) - 1
+    ggsw = np.full(p.ggsw_len(), -(1 << 16), dtype=np.int64)
+    got = api.external_product_batch(p, cts, ggsw)
+    for i in range(2):
+        assert np.array_equal(got[i], s.orc.external_product(cts[i], ggsw))
+
+
+def test_coordinate_product_chain(scenario):
+    from fhe_ram_b200 import api
+    s = scenario()
+    rng = np.random.default_rng(2)
+    cts = _rand_glwe(rng, s.params, 3)
+    addr = s.address(4321)
+    nd = len(s.params.base2d()[0])
+    ggsws = addr.data[: nd * s.params.ggsw_len()]
+    got = api.coordinate_product(s.params, cts, ggsws, nd)
+    for i in range(3):
+        assert np.array_equal(got[i], s.orc.coordinate_product(cts[i], ggsws, nd))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_automorphism_variants(scenario, gpu_keys, mode):
+    from fhe_ram_b200 import api
+    s = scenario()
+    keys = gpu_keys(s)
+    rng = np.random.default_rng(3 + mode)
+    cts = _rand_glwe(rng, s.params, 2)
+    for gi in (0, 1, 7, 11):
+        got = api.glwe_automorphism(s.params, keys, gi, mode, cts)
+        for i in range(2):
+            x = cts[i] if mode == 0 else s.orc.glwe_rsh(1, cts[i])
+            want = s.orc.automorphism(s.okeys, gi, mode, x)
+            assert np.array_equal(got[i], want), (mode, gi, i, np.count_nonzero(got[i] != want))
+
+
+def test_trace_matches_oracle(scenario, gpu_keys):
+    from fhe_ram_b200 import api
+    s = scenario()
+    keys = gpu_keys(s)
+    rng = np.random.default_rng(5)
+    cts = _rand_glwe(rng, s.params, 3)
+    got = api.glwe_trace(s.params, keys, cts)
+    for i in range(3):
+        assert np.array_equal(got[i], s.orc.trace(s.okeys, cts[i]))
+    got = api.glwe_trace(s.params, keys, cts, 3, 9)
+    assert np.array_equal(got[0], s.orc.trace(s.okeys, cts[0], 3, 9))
+
+
+@pytest.mark.parametrize("n", [1, 2, 8])
+def test_packer_matches_oracle(scenario, gpu_keys, n):
+    """GLWEPacker fed as src/ram.rs:424-449 does (bit-reversed order, None elsewhere)."""
+    from fhe_ram_b200 import api
+    s = scenario()
+    keys = gpu_keys(s)
+    rng = np.random.default_rng(6 + n)
+    cts = _rand_glwe(rng, s.params, n)
+    got = api.glwe_pack(s.params, keys, cts)
+    N, log_n = s.params.n(), s.params.log_n()
+    feed = []
+    for j in range(N):
+        jr = int(format(j, f"0{log_n}b")[::-1], 2)
+        feed.append(cts[jr] if jr < n else None)
+    want = s.orc.pack(s.okeys, feed)
+    assert np.array_equal(got, want), np.count_nonzero(got != want)
+
+
+def test_ggsw_invert_matches_oracle(scenario, gpu_keys):
+    from fhe_ram_b200 import api
+    s = scenario()
+    keys = gpu_keys(s)
+    addr = s.address(777)
+    L = s.params.ggsw_len()
+    got = api.ggsw_invert(s.params, keys, addr.data[: 2 * L])
+    for i in range(2):
+        want = s.orc.ggsw_automorphism_inv(s.okeys, addr.data[i * L:(i + 1) * L])
+        assert np.array_equal(got[i * L:(i + 1) * L], want), np.count_nonzero(got[i * L:(i + 1) * L] != want)
+
+
+@pytest.mark.parametrize("max_addr,word_size", [(1 << 13, 2), (1 << 12, 1), (1 << 10, 1), (1 << 14, 4)])
+def test_read_rpw_write_bit_exact(scenario, gpu_keys, max_addr, word_size):
+    """The acceptance scenario of examples/fhe-ram.rs:97-176, limb-for-limb against the oracle."""
+    s = scenario(max_addr, word_size)
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    oram = s.orc.ram_new(s.cts.copy())
+    idx = s.src.next_u32() % max_addr
+    addr = s.address(idx)
+
+    got = ram.read(addr, keys)
+    rc, want = s.orc.ram_read(oram, addr.data, s.okeys)
+    assert rc == 0 and np.array_equal(got, want), np.count_nonzero(got != want)
+    s.check_decrypt(got, idx)
+
+    got = ram.read_prepare_write(addr, keys)
+    rc, want = s.orc.ram_read_prepare_write(oram, addr.data, s.okeys)
+    assert rc == 0 and np.array_equal(got, want)
+    assert ram.state() and np.array_equal(ram.store(), s.orc.ram_store(oram))
+    if len(p.base2d()) > 1:
+        assert np.array_equal(ram.tree_store(), s.orc.ram_tree_store(oram))
+
+    value = s.src.fill_bytes(word_size)
+    w = np.stack([fr.encrypt_glwe(p, int(v), s.sk) for v in value])
+    ram.write(w, addr, keys)
+    assert s.orc.ram_write(oram, w.reshape(-1), addr.data, s.okeys) == 0
+    assert not ram.state()
+    assert np.array_equal(ram.store(), s.orc.ram_store(oram)), "RAM limbs differ after write"
+    if len(p.base2d()) > 1:
+        assert np.array_equal(ram.tree_store(), s.orc.ram_tree_store(oram))
+
+    data2 = s.data.copy()
+    data2[idx * word_size:(idx + 1) * word_size] = value
+    got = ram.read(addr, keys)
+    rc, want = s.orc.ram_read(oram, addr.data, s.okeys)
+    assert np.array_equal(got, want)
+    s.check_decrypt(got, idx, data2)
+    other = (idx + p.n() + 1) % max_addr
+    got = ram.read(s.address(other), keys)
+    s.check_decrypt(got, other, data2)
+    ram.close()
+
+
+def test_batched_reads_equal_single_reads(scenario, gpu_keys):
+    s = scenario()
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    idxs = [0, 1, p.n() - 1, p.n(), p.max_addr() - 1, 4242 % p.max_addr(), 77]
+    addrs = [s.address(i) for i in idxs]
+    batch = fr.Address.batch(p, addrs)
+    got = ram.read_batch(batch, keys)
+    oram = s.orc.ram_new(s.cts.copy())
+    for b, (i, a) in enumerate(zip(idxs, addrs)):
+        rc, want = s.orc.ram_read(oram, a.data, s.okeys)
+        assert np.array_equal(got[b], want), (b, i)
+        s.check_decrypt(got[b], i)
+        assert np.array_equal(ram.read(a, keys), want)
+    ram.close()
+
+
+def test_state_machine_and_errors(scenario, gpu_keys):
+    """assert!s of src/ram.rs:182-185,243,393-396,555-558 become error codes."""
+    s = scenario()
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    addr = s.address(3)
+    with pytest.raises(fr.FheRamError) as e:
+        ram.read(addr, keys)
+    assert e.value.code == -4
+    ram.load(s.cts)
+    w = np.stack([fr.encrypt_glwe(p, 1, s.sk) for _ in range(p.word_size())])
+    with pytest.raises(fr.FheRamError) as e:
+        ram.write(w, addr, keys)
+    assert e.value.code == -3
+    ram.read_prepare_write(addr, keys)
+    with pytest.raises(fr.FheRamError) as e:
+        ram.read(addr, keys)
+    assert e.value.code == -2
+    with pytest.raises(fr.FheRamError):
+        ram.write(w[:1], addr, keys)
+    ram.write(w, addr, keys)
+    ram.read(addr, keys)
+    with pytest.raises(fr.FheRamError):
+        ram.encrypt_sk(s.data[:-1], s.sk, s.xa, s.xe)
+    ram.close()
+
+
+def test_full_size_2pow18_properties(scenario, gpu_keys):
+    """BASELINE.json size (2^18 x 4 B): size-independent properties -- every read decrypts to the
+    plaintext word, write/read-back round trip, untouched words survive a write."""
+    s = scenario(1 << 18, 4, 9)
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    idxs = [0, 4095, 4096, (1 << 18) - 1, 123457]
+    batch = fr.Address.batch(p, [s.address(i) for i in idxs])
+    got = ram.read_batch(batch, keys)
+    for b, i in enumerate(idxs):
+        s.check_decrypt(got[b], i)
+    addr = s.address(200001)
+    s.check_decrypt(ram.read_prepare_write(addr, keys), 200001)
+    value = np.array([1, 2, 100, 127], dtype=np.uint8)
+    w = np.stack([fr.encrypt_glwe(p, int(v), s.sk) for v in value])
+    ram.write(w, addr, keys)
+    data2 = s.data.copy()
+    data2[200001 * 4:200001 * 4 + 4] = value
+    s.check_decrypt(ram.read(addr, keys), 200001, data2)
+    for i in (200000, 200002, 200001 - 4096, 5):
+        s.check_decrypt(ram.read(s.address(i), keys), i, data2)
+    ram.close()
