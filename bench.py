@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- FHE-RAM hot-path benchmark (BASELINE.json metric: batched reads/s at 2^18 x 4 B,
+plus single read / read_prepare_write / write latency).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+A "step" is one batch of B independent encrypted-address reads (BASELINE.json config 3, B = 1024)
+against a RAM of max_addr = 2^18 words x 4 bytes (README.md:17-34 parameters).  `value` is measured
+with keys, RAM and prepared addresses resident in HBM; `e2e` runs the same batch through the C ABI
+with HOST buffers (address upload + on-device prepare + read + result download in the timed
+region).  N > 1: the RAM is sharded by polynomial index mod N, one process per GPU,
+partial ciphertexts exchanged with NCCL; the global batch stays B ("strong" scaling).
+--impl reference times the CPU restatement of the reference's FFT64 path (oracle/, kind "port":
+the reference itself cannot be built here -- no Rust toolchain, Poulpy un-vendored).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# algorithmic work per operation (SURVEY.md 8d / BASELINE.md 4)
+F_EXT = 2_363_392   # flop per external product (6 fwd + 8 inv FFT of 2048 pts, 6x8 contraction)
+F_KS = 1_632_256    # flop per key-switch automorphism (3 + 8 FFT, 3x8 contraction)
+B_EXT = 1.5 * 2**20 + 2 * 96 * 2**10   # bytes per ext product: prepared GGSW + ct in + ct out (int32)
+B_KS = 0.75 * 2**20                    # bytes per key-switch: prepared key (ct stays in shared memory)
+
+
+def op_model(max_addr, word_size, base2d, n=4096):
+    """(ext, ks) per read (src/ram.rs:382-459) and per write (:226-294, GGSW inversions excluded)."""
+    g = max(1, max_addr // n)
+    d0 = len(base2d[0])
+    d1 = len(base2d[1]) if len(base2d) > 1 else 0
+    lg = (g - 1).bit_length() if g > 1 else 0
+    pack = 0 if g == 1 else g * (12 - lg) + (g - 1)
+    read = (word_size * (g * d0 + d1), word_size * (pack + 12))
+    write = (word_size * (g * d0 + d1), word_size * (12 + (2 * g * 12 if g > 1 else 0)))
+    return read, write
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_addresses(fr, params, sk, idxs, threads):
+    """Address::encrypt_sk (client side, CPU) for every index, on `threads` host threads."""
+    out = np.zeros((len(idxs), params.n_ggsw() * params.ggsw_len()), dtype=np.int64)
+
+    def one(j):
+        a = fr.Address.alloc(params)
+        a.data = out[j]
+        a.encrypt_sk(params, int(idxs[j]), sk, fr.Source(1000 + j), fr.Source(5000 + j))
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(len(idxs))))
+    return out
+
+
+def cpu_baseline(max_addr, word_size, k_pt, evk, cts, addr_limbs, sk_data, data, idxs, n_reads, threads):
+    """Times the oracle's FFT64 restatement of Ram::read (the CPU port) on a bounded sample."""
+    from oracle.oracle import Oracle
+    orc = Oracle(backend="fft64", max_addr=max_addr, word_size=word_size, k_pt=k_pt)
+    keys = orc.keys_prepare(evk.atk_glwe, evk.gglwe_to_ggsw_key, evk.atk_ggsw_inv)
+    ram = orc.ram_new(cts)
+    t0 = time.perf_counter()
+    rc, out = orc.ram_read_many(ram, np.ascontiguousarray(addr_limbs[:n_reads]).reshape(-1), n_reads, keys, threads)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    for b in range(n_reads):  # the port must decrypt correctly too
+        for i in range(word_size):
+            want = orc.cast_u8_to_signed(int(data[i + word_size * idxs[b]]), min(8, k_pt))
+            v, noise = orc.decrypt_glwe(out[b, i], sk_data, want)
+            assert v == want, "cpu port decrypt mismatch"
+    return n_reads / dt, dt, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--max-addr-log2", type=int, default=18)
+    ap.add_argument("--word-size", type=int, default=4)
+    ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the cpu_baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    max_addr, ws, k_pt = 1 << args.max_addr_log2, args.word_size, 9
+    from oracle.oracle import host_threads
+    threads = host_threads()
+    workload = f"{args.batch} independent encrypted-address reads, RAM 2^{args.max_addr_log2} x {ws} B (N=4096, base2k=17)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import __graft_entry__ as g
+        g.build()
+        import fhe_ram_b200 as fr
+        params = fr.Parameters.readme(max_addr=max_addr, word_size=ws, k_pt=k_pt)
+        sk, evk = fr.gen_keys(params)
+        data = fr.Source(5).fill_bytes(max_addr * ws)
+        import ctypes as C
+        from fhe_ram_b200 import api
+        cts = np.zeros(ws * params.n_glwe() * params.glwe_len(), dtype=np.int64)
+        xa, xe = fr.Source(11), fr.Source(12)
+        api._check(api.lib().fheram_encrypt_ram(C.byref(params.c), data.ctypes.data_as(api._PU8), api._p(sk.data),
+                                                xa.h, xe.h, api._p(cts)))
+        n_reads = args.cpu_reads or max(1, threads // ws)
+        rng = np.random.default_rng(7)
+        idxs = rng.integers(0, max_addr, size=n_reads)
+        addrs = make_addresses(fr, params, sk, idxs, threads)
+        vals = []
+        for _ in range(args.warmup if args.warmup < 1 else 1):
+            cpu_baseline(max_addr, ws, k_pt, evk, cts, addrs, sk.data, data, idxs, n_reads, threads)
+        for _ in range(args.steps):
+            v, dt, _ = cpu_baseline(max_addr, ws, k_pt, evk, cts, addrs, sk.data, data, idxs, n_reads, threads)
+            vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals]))
+        ms = float(np.mean([x[1] for x in vals])) * 1e3
+        sample = f"{n_reads} Ram::read per step (1 warm-up + {args.steps} timed), oracle FFT64 port, {threads} threads"
+        print(json.dumps({
+            "impl": "reference", "metric": "batched_reads_per_s", "value": v, "unit": "reads/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference binary cannot be built offline (no cargo/rustc; Poulpy path dependency "
+                    "absent, Cargo.toml:7-10); README.md:36 quotes 450 ms per read on an i9-12900K, 1 thread",
+        }))
+        return
+
+    import torch
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    import fhe_ram_b200 as fr
+    from fhe_ram_b200 import api
+
+    device = local_rank if world > 1 else 0
+    torch.cuda.set_device(device)
+    params = fr.Parameters.readme(device=device, max_addr=max_addr, word_size=ws, k_pt=k_pt)
+    sk, evk = fr.gen_keys(params)                       # same seeds on every rank: identical keys
+    keys = fr.EvaluationKeysPrepared.alloc(params).prepare(evk)
+    data = fr.Source(5).fill_bytes(max_addr * ws)
+    import ctypes as C
+    cts = np.zeros(ws * params.n_glwe() * params.glwe_len(), dtype=np.int64)
+    xa, xe = fr.Source(11), fr.Source(12)
+    api._check(api.lib().fheram_encrypt_ram(C.byref(params.c), data.ctypes.data_as(api._PU8), api._p(sk.data),
+                                            xa.h, xe.h, api._p(cts)))
+    B = args.batch
+    rng = np.random.default_rng(7)
+    idxs = rng.integers(0, max_addr, size=B)
+    t0 = time.perf_counter()
+    addr_limbs = make_addresses(fr, params, sk, idxs, threads)
+    t_addr = time.perf_counter() - t0
+    stream = torch.cuda.ExternalStream(params.stream(), device=device)
+    L = params.glwe_len()
+
+    if world > 1:
+        from fhe_ram_b200.sharded import ShardedRam
+        sram = ShardedRam(params, rank, world, cts)
+        run_resident, run_e2e, check = sram.bench_closures(addr_limbs, keys, B)
+    else:
+        ram = fr.Ram.new(params)
+        ram.load(cts)
+        addr_res = fr.Address.from_limbs(params, addr_limbs, B)
+        addr_res.device()
+        api.host_register(addr_limbs)
+        out_host = np.zeros((B, ws, L), dtype=np.int64)
+        api.host_register(out_host)
+
+        def run_resident():
+            return ram.read_batch_device(addr_res, keys)
+
+        def run_e2e():
+            a = fr.Address.from_limbs(params, addr_limbs, B)   # host int64 limbs -> device + prepare
+            api._check(api.lib().fheram_ram_read_batch(ram.h, a.device(), keys.h, api._p(out_host)))
+            a.close()
+            return out_host
+
+        def check(out):
+            for b in (0, B // 2, B - 1):
+                for i in range(ws):
+                    want = fr.cast_u8_to_signed(int(data[i + ws * idxs[b]]), 8)
+                    v, noise = fr.decrypt_glwe(params, out[b, i], want, sk)
+                    assert v == want and noise < -(k_pt + 1), (b, i, v, want, noise)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        params.synchronize()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=f"cuda:{device}")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up, then the device-resident timed region --------------------------------
+    for _ in range(args.warmup):
+        run_resident()
+    sampler = ClockSampler(device)
+    sampler.start()
+    params.profile(True)
+    l0 = params.launch_count()
+    ms_total = timed(run_resident, args.steps)
+    launches = params.launch_count() - l0
+    prof = params.profile_get()
+    params.profile(False)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = B / (ms_step * 1e-3)
+
+    # correctness of what was timed (decrypt a sample of the batch)
+    if world == 1:
+        d_out = run_resident()
+        res = np.zeros((B, ws, L), dtype=np.int64)
+        api._check(api.lib().fheram_download_glwe(params.module(), d_out, B * ws, api._p(res)))
+        check(res)
+
+    # ---- end-to-end through the C ABI with host buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(min(args.warmup, 2)):
+            run_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ms_e2e = timed(run_e2e, args.steps)
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(ms_e2e, 0.0)
+        # the e2e path synchronises on the host, so wall clock and event time agree; report the event time
+        out = run_e2e()
+        if world == 1:
+            check(out)
+        e2e = {"value": B / (ms_e2e / args.steps * 1e-3), "unit": "reads/s",
+               "h2d_bytes_per_step": int(addr_limbs.nbytes), "d2h_bytes_per_step": int(B * ws * L * 8),
+               "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall / args.steps}
+
+    if rank != 0:
+        return
+
+    # ---- single-op latencies (BASELINE metric: read / write ms at 2^18 x 4 B, 1 GPU) ----
+    lat = {}
+    if world == 1:
+        a1 = fr.Address.from_limbs(params, addr_limbs[0], 1)
+        a1.device()
+        one = np.zeros((1, ws, L), dtype=np.int64)
+
+        def t_call(fn, reps=5):
+            ts = []
+            for _ in range(reps):
+                params.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                params.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            return float(np.median(ts))
+
+        lat["read_ms"] = t_call(lambda: api._check(api.lib().fheram_ram_read(ram.h, a1.device(), keys.h, api._p(one))))
+        wv = np.stack([fr.encrypt_glwe(params, int(v), sk) for v in (1, 2, 3, 4)[:ws]])
+        rpw, wr = [], []
+        for _ in range(3):
+            params.synchronize(); t0 = time.perf_counter()
+            ram.read_prepare_write(a1, keys)
+            params.synchronize(); rpw.append((time.perf_counter() - t0) * 1e3)
+            t0 = time.perf_counter()
+            ram.write(wv, a1, keys)
+            params.synchronize(); wr.append((time.perf_counter() - t0) * 1e3)
+        lat["read_prepare_write_ms"] = float(np.median(rpw))
+        lat["write_ms"] = float(np.median(wr))
+
+    # ---- roofline of the dominant kernel (CUDA events over the timed region) -------------
+    (r_ext, r_ks), _ = op_model(max_addr, ws, params.base2d())
+    fp64_peak = params.fp64_peak_tflops()
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    cls_flop = {"ext": F_EXT, "trace": F_KS, "combine2": F_KS}
+    cls_bytes = {"ext": B_EXT, "trace": B_KS, "combine2": B_KS + 3 * 96 * 2**10}
+    dom = max(("ext", "trace", "combine2"), key=lambda k: prof[k]["ms"])
+    pd = prof[dom]
+    ach_tf = pd["ops"] * cls_flop[dom] / (pd["ms"] * 1e-3) / 1e12 if pd["ms"] > 0 else 0.0
+    ach_gb = pd["ops"] * cls_bytes[dom] / (pd["ms"] * 1e-3) / 1e9 if pd["ms"] > 0 else 0.0
+    shares = {k: round(prof[k]["ms"] / max(1e-9, sum(prof[c]["ms"] for c in prof)), 4) for k in prof}
+    roofline = {
+        "bound": "fp64", "kernel": f"k_vmp<{dom}>", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "peak_source": "fp64 FMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry; "
+                       "nominal 37.2 TFLOP/s = 148 SM x 64 FMA x 2 x 1.965 GHz)",
+        "avg_launch_ms": pd["ms"] / max(1, pd["launches"]), "launches": pd["launches"],
+        "ops_per_launch": pd["ops"] / max(1, pd["launches"]), "flop_per_op": cls_flop[dom],
+        "kernel_time_share": shares,
+        "hbm_view": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ach_gb / hbm_peak, "bytes_per_op": cls_bytes[dom],
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+        "whole_read": {"flop_per_read": r_ext * F_EXT + r_ks * F_KS,
+                       "achieved_tflops": value * (r_ext * F_EXT + r_ks * F_KS) / 1e12,
+                       "frac_of_fp64_peak": value * (r_ext * F_EXT + r_ks * F_KS) / 1e12 / fp64_peak if fp64_peak else None},
+    }
+
+    # ---- CPU baseline (oracle port) on a bounded sample ----------------------------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        n_reads = args.cpu_reads or max(1, threads // ws)
+        v, dt, _ = cpu_baseline(max_addr, ws, k_pt, evk, cts, addr_limbs, sk.data, data, idxs, n_reads, threads)
+        cpu = {"value": v, "unit": "reads/s", "cores": threads, "kind": "port",
+               "sample": f"{n_reads} Ram::read of the same workload in {dt:.1f} s, oracle FFT64 restatement "
+                         f"(not the reference binary), {threads} threads",
+               "readme_reference": "450 ms/read, 1200 ms/write, i9-12900K 1 thread (README.md:36)"}
+
+    line = {
+        "metric": "batched_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload, "max_addr": max_addr, "word_size": ws, "k_pt": k_pt, "batch": B,
+                   "parallelism": f"ram sharded by polynomial index mod {world}" if world > 1 else "single gpu",
+                   "l2": "inputs larger than L2: prepared addresses %.1f GiB + work arenas" % (B * params.n_ggsw() * 1.5 / 1024),
+                   "address_gen_s": round(t_addr, 2)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu, **lat,
+    }
+    if "read_ms" in lat:
+        line["vs_readme_read"] = 450.0 / lat["read_ms"]
+        line["vs_readme_write"] = 1200.0 / lat["write_ms"]
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,11 @@ SIGNATURES = {
     "fheram_ctx_synchronize": (C.c_int, [_V]),
     "fheram_ctx_stream": (_V, [_V]),
     "fheram_ctx_launch_count": (C.c_uint64, [_V]),
+    "fheram_ctx_profile": (C.c_int, [_V, C.c_int]),
+    "fheram_ctx_profile_get": (C.c_int, [_V, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fheram_fp64_peak_probe": (C.c_int, [_V, C.c_int, C.POINTER(C.c_double)]),
+    "fheram_host_register": (C.c_int, [_V, C.c_size_t]),
+    "fheram_host_unregister": (C.c_int, [_V]),
     "fheram_keys_prepare": (C.c_int, [_V, _P64, _P64, _P64, _PV]),
     "fheram_keys_destroy": (C.c_int, [_V]),
     "fheram_address_load": (C.c_int, [_V, _P64, _PV]),
@@ -219,18 +224,43 @@ class Parameters:
     def stream(self) -> int:
         return int(lib().fheram_ctx_stream(self.module()) or 0)
 
+    def profile(self, enable: bool):
+        _check(lib().fheram_ctx_profile(self.module(), 1 if enable else 0))
+
+    def profile_get(self):
+        """per kernel class (ext, trace, combine2, other): (ms, launches, ops)"""
+        ms = (C.c_double * 4)()
+        ln = (C.c_uint64 * 4)()
+        ops = (C.c_uint64 * 4)()
+        _check(lib().fheram_ctx_profile_get(self.module(), ms, ln, ops))
+        names = ("ext", "trace", "combine2", "other")
+        return {n: {"ms": ms[i], "launches": int(ln[i]), "ops": int(ops[i])} for i, n in enumerate(names)}
+
+    def fp64_peak_tflops(self, reps: int = 5) -> float:
+        v = C.c_double()
+        _check(lib().fheram_fp64_peak_probe(self.module(), reps, C.byref(v)))
+        return float(v.value)
+
     def close(self):
         if self._ctx is not None:
             lib().fheram_ctx_destroy(self._ctx)
             self._ctx = None
 
 
+def host_register(a: np.ndarray):
+    _check(lib().fheram_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+
+def host_unregister(a: np.ndarray):
+    _check(lib().fheram_host_unregister(a.ctypes.data_as(C.c_void_p)))
+
+
 class Source:
     """poulpy_hal::source::Source::new(seed) (examples/fhe-ram.rs:41-43)."""
 
     def __init__(self, seed):
-        if isinstance(seed, int):
-            seed = bytes([seed] * 32)
+        if isinstance(seed, int):  # [x; 32] as the example's seeds, or a 256-bit integer
+            seed = bytes([seed] * 32) if 0 <= seed < 256 else int(seed).to_bytes(32, "little")
         self.h = lib().fheram_source_new((C.c_uint8 * 32)(*seed))
 
     def next_u32(self) -> int:

@@ -164,6 +164,12 @@ struct fheram_ctx {
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
   DevBuf opbuf[3];  // op-level entry points
+  // per-kernel-class CUDA-event timing (fheram_ctx_profile)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct EvRec { int cls; size_t e0, e1; uint64_t items, steps; };
+  std::vector<EvRec> ev_recs;
+  size_t ev_used = 0;
   long ct_stride() const { return (long)2 * d.size_ct * d.n; }          // ints per GLWE(k_ct)
   long ggsw_raw_len() const { return (long)d.dnum_ct * 4 * d.size_addr * d.n; }
   long ggsw_prep_len() const { return (long)d.dnum_ct * 2 * 2 * d.size_addr * kM; }  // double2
@@ -285,6 +291,75 @@ extern "C" int fheram_ctx_synchronize(fheram_ctx* c) {
 extern "C" void* fheram_ctx_stream(fheram_ctx* c) { return (void*)c->stream; }
 extern "C" uint64_t fheram_ctx_launch_count(const fheram_ctx* c) { return c->launches; }
 
+// ---- measurement helpers ----------------------------------------------------------------
+extern "C" int fheram_ctx_profile(fheram_ctx* c, int enable) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  c->profile = enable != 0;
+  c->ev_recs.clear();
+  c->ev_used = 0;
+  return 0;
+}
+// per class (0 ext chain, 1 trace/key-switch chain, 2 two-sided combine, 3 other):
+// ms[c] = summed device time, launches[c], ops[c] = sum over launches of items*steps
+extern "C" int fheram_ctx_profile_get(fheram_ctx* c, double ms[4], uint64_t launches[4], uint64_t ops[4]) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; i++) { ms[i] = 0; launches[i] = 0; ops[i] = 0; }
+  for (auto& r : c->ev_recs) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, c->ev_pool[r.e0], c->ev_pool[r.e1]));
+    ms[r.cls] += t; launches[r.cls]++; ops[r.cls] += r.items * r.steps;
+  }
+  return 0;
+}
+
+__global__ void k_fp64_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, b = 1e-7;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+      a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+// FP64 FMA-pipe peak of this GPU (MEASURED_PEAKS.json has no FP64 entry): best of `reps`
+extern "C" int fheram_fp64_peak_probe(fheram_ctx* c, int reps, double* tflops) {
+  CU(cudaSetDevice(c->device));
+  const int blocks = c->sm_count * 4, threads = 512, iters = 4096;
+  double* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int r = 0; r < reps + 1; r++) {
+    CU(cudaEventRecord(e0, c->stream));
+    k_fp64_probe<<<blocks, threads, 0, c->stream>>>(d, iters);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = (double)blocks * threads * iters * 64 * 2 / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
+  CU(cudaFree(d));
+  *tflops = best;
+  return 0;
+}
+extern "C" int fheram_host_register(void* p, size_t bytes) {
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int fheram_host_unregister(void* p) {
+  CU(cudaHostUnregister(p));
+  return 0;
+}
+
 // --------------------------------------------------------------------------------------
 // host <-> device limb conversion
 // --------------------------------------------------------------------------------------
@@ -337,11 +412,27 @@ static VmpArgs base_args(fheram_ctx* c, int n_items, const int* src, int* dst, l
   a.tw = c->tw;
   return a;
 }
+static size_t prof_event(fheram_ctx* c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+  return c->ev_used++;
+}
+enum KClass { KC_EXT = 0, KC_TRACE = 1, KC_COMBINE2 = 2, KC_OTHER = 3, KC_COUNT = 4 };
 template <typename K>
-static int launch(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem) {
+static int launch(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem, int cls = KC_OTHER) {
   if (a.n_items <= 0) return 0;
   int grid = a.n_items < c->sm_count ? a.n_items : c->sm_count;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
   kernel<<<grid, kThreads, smem, c->stream>>>(a);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -458,7 +549,7 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
   a.n_steps = n_dig;
   for (int s = 0; s < n_dig; s++) a.mat[s] = mats + (size_t)s * c->ggsw_prep_len();
   a.mat_div = mat_div; a.mat_stride = mat_stride;
-  return launch(c, K_EXT, a, smem_bytes(3, 2, false));
+  return launch(c, K_EXT, a, smem_bytes(3, 2, false), KC_EXT);
 }
 // chain of { glwe_rsh(1); automorphism_add with trace key i } for i in [g0, g1)
 // (glwe_trace_inplace, and the one-sided levels of GLWEPacker::combine)
@@ -481,7 +572,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
-  return launch(c, K_TRACE, a, smem_bytes(3, 1, true));
+  return launch(c, K_TRACE, a, smem_bytes(3, 1, true), KC_TRACE);
 }
 // GLWEPacker::combine, both operands present, at tree level `level` (0-based absolute):
 // in[2i], in[2i+1] -> out[i]
@@ -491,7 +582,7 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.mat[0] = k->atk + (size_t)level * c->atk_prep_len();
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
-  return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true));
+  return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }
 
 // GLWEPacker over `width` inputs per group (width a power of two), feed order = index order

@@ -83,6 +83,17 @@ void *fheram_ctx_stream(fheram_ctx *ctx);
 /* number of kernels launched by this context so far */
 uint64_t fheram_ctx_launch_count(const fheram_ctx *ctx);
 
+/* measurement: CUDA-event timing of every vmp-class launch on the context stream.
+ * classes: 0 external-product chain, 1 key-switch (trace / one-sided combine) chain,
+ * 2 two-sided packer combine, 3 other.  ops = sum over launches of items x chain steps. */
+int fheram_ctx_profile(fheram_ctx *ctx, int enable);
+int fheram_ctx_profile_get(fheram_ctx *ctx, double ms[4], uint64_t launches[4], uint64_t ops[4]);
+/* FP64 FMA peak of the device in TFLOP/s (dependent-chain DFMA probe, best of reps) */
+int fheram_fp64_peak_probe(fheram_ctx *ctx, int reps, double *tflops);
+/* pin / unpin a caller-owned host buffer (cudaHostRegister) so uploads run at PCIe speed */
+int fheram_host_register(void *p, size_t bytes);
+int fheram_host_unregister(void *p);
+
 /* ---- EvaluationKeysPrepared::alloc + ::prepare (src/keys.rs:34-71): uploads the raw keys and
  * runs vmp_prepare on the device; atk_glwe = the log_n trace keys in
  * fheram_trace_galois_element order, tsk = GGLWEToGGSWKey, atk_inv = automorphism key p=-1 */
