@@ -215,9 +215,21 @@ def main():
     L = params.glwe_len()
 
     if world > 1:
-        from fhe_ram_b200.sharded import ShardedRam
-        sram = ShardedRam(params, rank, world, cts)
-        run_resident, run_e2e, check = sram.bench_closures(addr_limbs, keys, B)
+        from fhe_ram_b200.sharded import GpuEngine, ShardedRam
+        assert B % world == 0, "--batch must be a multiple of the number of GPUs"
+        sram = ShardedRam(GpuEngine(params, rank, world, cts), rank, world)
+        api.host_register(addr_limbs)
+        out_host = np.zeros((B // world, ws, L), dtype=np.int64)
+        api.host_register(out_host)
+        run_resident, run_e2e = sram.bench_closures(api, addr_limbs, keys, B, out_host)
+        first = rank * (B // world)
+
+        def check(out):
+            for b in (0, B // world - 1):
+                for i in range(ws):
+                    want = fr.cast_u8_to_signed(int(data[i + ws * idxs[first + b]]), 8)
+                    v, noise = fr.decrypt_glwe(params, out[b, i], want, sk)
+                    assert v == want and noise < -(k_pt + 1), (b, i, v, want, noise)
     else:
         ram = fr.Ram.new(params)
         ram.load(cts)
@@ -266,8 +278,9 @@ def main():
         return ms
 
     # ---- warm-up, then the device-resident timed region --------------------------------
-    for _ in range(args.warmup):
-        run_resident()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            run_resident()
     sampler = ClockSampler(device)
     sampler.start()
     params.profile(True)
@@ -286,26 +299,32 @@ def main():
         res = np.zeros((B, ws, L), dtype=np.int64)
         api._check(api.lib().fheram_download_glwe(params.module(), d_out, B * ws, api._p(res)))
         check(res)
+    else:
+        with torch.cuda.stream(stream):
+            check(run_e2e())
 
     # ---- end-to-end through the C ABI with host buffers --------------------------------
     e2e = None
     if not args.no_e2e:
-        for _ in range(min(args.warmup, 2)):
-            run_e2e()
+        with torch.cuda.stream(stream):
+            for _ in range(min(args.warmup, 2)):
+                run_e2e()
         barrier()
         t0 = time.perf_counter()
         ms_e2e = timed(run_e2e, args.steps)
         wall = (time.perf_counter() - t0) * 1e3
         ms_e2e = max(ms_e2e, 0.0)
         # the e2e path synchronises on the host, so wall clock and event time agree; report the event time
-        out = run_e2e()
-        if world == 1:
-            check(out)
+        with torch.cuda.stream(stream):
+            out = run_e2e()
+        check(out)
         e2e = {"value": B / (ms_e2e / args.steps * 1e-3), "unit": "reads/s",
                "h2d_bytes_per_step": int(addr_limbs.nbytes), "d2h_bytes_per_step": int(B * ws * L * 8),
                "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall / args.steps}
 
     if rank != 0:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
         return
 
     # ---- single-op latencies (BASELINE metric: read / write ms at 2^18 x 4 B, 1 GPU) ----
@@ -367,7 +386,7 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
         "whole_read": {"flop_per_read": r_ext * F_EXT + r_ks * F_KS,
                        "achieved_tflops": value * (r_ext * F_EXT + r_ks * F_KS) / 1e12,
-                       "frac_of_fp64_peak": value * (r_ext * F_EXT + r_ks * F_KS) / 1e12 / fp64_peak if fp64_peak else None},
+                       "frac_of_fp64_peak": value * (r_ext * F_EXT + r_ks * F_KS) / 1e12 / (fp64_peak * world) if fp64_peak else None},
     }
 
     # ---- CPU baseline (oracle port) on a bounded sample ----------------------------------
@@ -396,6 +415,9 @@ def main():
         line["vs_readme_read"] = 450.0 / lat["read_ms"]
         line["vs_readme_write"] = 1200.0 / lat["write_ms"]
     print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -94,7 +94,7 @@ SIGNATURES = {
     "fheram_ram_read_batch_device": (C.c_int, [_V, _V, _V, _PV]),
     "fheram_download_glwe": (C.c_int, [_V, _V, C.c_int, _P64]),
     "fheram_ram_read_local_device": (C.c_int, [_V, _V, _V, _PV]),
-    "fheram_ram_read_finish_device": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, _V, _PV]),
+    "fheram_ram_read_finish_device": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, C.c_int, _V, _PV]),
     "fheram_ram_rpw_local_device": (C.c_int, [_V, _V, _V, _PV]),
     "fheram_ram_rpw_finish_device": (C.c_int, [_V, _V, _V, _V, _PV]),
     "fheram_external_product_batch": (C.c_int, [_V, _P64, C.c_int, _P64, _P64]),

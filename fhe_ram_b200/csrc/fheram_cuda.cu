@@ -879,12 +879,13 @@ extern "C" int fheram_ram_read_local_device(fheram_ram* r, const fheram_address*
 }
 extern "C" int fheram_ram_read_finish_device(fheram_ram* r, const int32_t* d_gathered, int n_total,
                                              int first, int count, const fheram_address* addr,
-                                             const fheram_keys* k, const int32_t** d_out) {
+                                             int addr_first, const fheram_keys* k, const int32_t** d_out) {
   if (!r || !d_gathered || !addr || !k || !d_out) return fail(FHERAM_ERR_INVALID, "null argument");
-  if (first < 0 || count < 0 || first + count > n_total || n_total != addr->count)
+  if (first < 0 || count < 0 || first + count > n_total || addr_first < 0 ||
+      addr_first + first + count > addr->count)
     return fail(FHERAM_ERR_INVALID, "bad read range");
   CU(cudaSetDevice(r->c->device));
-  TRY(ram_finish_stage(r, d_gathered, n_total, first, count, addr, 0, k, false));
+  TRY(ram_finish_stage(r, d_gathered, n_total, first, count, addr, addr_first, k, false));
   *d_out = (const int32_t*)r->result.p;
   return 0;
 }

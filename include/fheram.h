@@ -151,12 +151,13 @@ int fheram_download_glwe(fheram_ctx *ctx, const int32_t *d_in, int n_glwe, int64
 int fheram_ram_create_sharded(fheram_ctx *ctx, int shard, int n_shards, fheram_ram **out);
 int fheram_ram_read_local_device(fheram_ram *r, const fheram_address *addr, const fheram_keys *k,
                                  const int32_t **d_partial);
-/* d_gathered: [n_shards][n_local][word_size] GLWE partials (rank-major); finishes reads
- * [first, first+count) of the batch: top log2(n_shards) packer levels, second coordinate,
- * trace.  Result in the result arena, [count][word_size] GLWE. */
+/* d_gathered: [n_shards][n_total][word_size] GLWE partials (rank-major); finishes entries
+ * [first, first+count) of it: top log2(n_shards) packer levels, second coordinate, trace.
+ * Entry i belongs to address addr_first + i of `addr`.  Result in the result arena,
+ * [count][word_size] GLWE. */
 int fheram_ram_read_finish_device(fheram_ram *r, const int32_t *d_gathered, int n_total,
                                   int first, int count, const fheram_address *addr,
-                                  const fheram_keys *k, const int32_t **d_out);
+                                  int addr_first, const fheram_keys *k, const int32_t **d_out);
 
 /* read_prepare_write on a (possibly sharded) RAM, device-resident.  rpw_local rotates the local
  * polynomials in place (src/ram.rs:502-504) and packs them; after the all-gather every rank calls

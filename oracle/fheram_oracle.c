@@ -879,6 +879,16 @@ static void pack_core(const orc_ctx *c, const orc_keys *k, const i64 *a, accum *
     pack_core(c, k, prev->value ? prev->data : NULL, accs, i + 1);
   }
 }
+/* one GLWEPacker::combine at tree level `level` on an accumulator that holds a value (a, updated
+ * in place) and an optional second operand b: exposed so tests can restate the level-parallel
+ * schedule of the GPU path (and its sharded variant) with oracle arithmetic. */
+void orc_packer_combine(const orc_ctx *c, const orc_keys *k, int level, int64_t *a, const int64_t *b) {
+  accum acc;
+  acc.data = a;
+  acc.value = 1;
+  acc.control = 1;
+  packer_combine(c, k, &acc, b, level);
+}
 void orc_packer_add(orc_packer *p, const orc_keys *k, const int64_t *g) {
   assert(p->counter < p->c->n);
   pack_core(p->c, k, g, p->acc, 0);

@@ -140,6 +140,8 @@ orc_packer *orc_packer_new(const orc_ctx *c);
 void orc_packer_free(orc_packer *p);
 void orc_packer_add(orc_packer *p, const orc_keys *k, const int64_t *glwe_or_null);
 void orc_packer_flush(orc_packer *p, int64_t *out);
+/* GLWEPacker::combine at tree level `level`: a (holds a value) updated in place, b may be NULL */
+void orc_packer_combine(const orc_ctx *c, const orc_keys *k, int level, int64_t *a, const int64_t *b);
 /* GGSW(X^i) -> GGSW(X^-i) (coordinate_prepared.rs:121-142, raw output before prepare) */
 void orc_ggsw_automorphism_inv(const orc_ctx *c, const orc_keys *k, const int64_t *in,
                                int64_t *out);

@@ -95,6 +95,7 @@ class Oracle:
             "orc_packer_new": (V, [V]), "orc_packer_free": (None, [V]),
             "orc_packer_add": (None, [V, V, _P64]), "orc_packer_flush": (None, [V, _P64]),
             "orc_ggsw_automorphism_inv": (None, [V, V, _P64, _P64]),
+            "orc_packer_combine": (None, [V, V, C.c_int, _P64, _P64]),
             "orc_ram_new": (V, [V]), "orc_ram_free": (None, [V]),
             "orc_ram_load": (None, [V, _P64]), "orc_ram_store": (None, [V, _P64]),
             "orc_ram_tree_store": (None, [V, _P64]), "orc_ram_state": (C.c_int, [V]),
@@ -264,6 +265,12 @@ class Oracle:
         out = np.zeros(self.glwe_len, dtype=np.int64)
         self.lib.orc_packer_flush(pk, _p(out))
         self.lib.orc_packer_free(pk)
+        return out
+
+    def packer_combine(self, keys, level, a, b=None):
+        """GLWEPacker::combine at `level`; returns the updated accumulator."""
+        out = np.array(a, dtype=np.int64, copy=True)
+        self.lib.orc_packer_combine(self.ctx, keys, level, _p(out), None if b is None else _p(np.ascontiguousarray(b)))
         return out
 
     def ggsw_automorphism_inv(self, keys, ggsw):
