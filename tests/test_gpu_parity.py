@@ -298,3 +298,14 @@ def test_sharded_stages_on_one_gpu(scenario, gpu_keys, n_shards):
         assert np.array_equal(r.tree_store(), ref.tree_store())
         r.close()
     ref.close()
+
+
+def test_cpp_host_layer_runs_the_example_scenario(built):
+    """fhe_ram_b200/cpp/example_fhe_ram = examples/fhe-ram.rs:34-177 through fheram.hpp (the
+    compiled-language mirror of the Rust API): exits 0 only if every decrypt/noise assert holds."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "fhe_ram_b200" / "cpp" / "example_fhe_ram"
+    r = subprocess.run([str(exe), "14"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "READ Elapsed time" in r.stdout and "WRITE Elapsed time" in r.stdout and r.stdout.strip().endswith("OK")
