@@ -164,6 +164,7 @@ struct fheram_ctx {
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
   DevBuf opbuf[3];  // op-level entry points
+  long long* d_phase = nullptr;  // per-CTA phase cycle counters (fheram_debug_phase_cycles)
   // per-kernel-class CUDA-event timing (fheram_ctx_profile)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -351,6 +352,27 @@ extern "C" int fheram_fp64_peak_probe(fheram_ctx* c, int reps, double* tflops) {
   *tflops = best;
   return 0;
 }
+// debug: enable (1) / read-and-disable (0) per-phase cycle counters of the vmp kernels; out[8] =
+// cycles summed over CTAs for phases {prologue, fwd pass 1, fwd warp passes, contraction, inverse,
+// epilogue, rest, unused}
+extern "C" int fheram_debug_phase_cycles(fheram_ctx* c, int enable, long long out[8]) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  const size_t n = (size_t)c->sm_count * 8;
+  if (enable) {
+    if (!c->d_phase) CU(cudaMalloc(&c->d_phase, sizeof(long long) * n));
+    CU(cudaMemset(c->d_phase, 0, sizeof(long long) * n));
+    return 0;
+  }
+  if (!c->d_phase) return fail(FHERAM_ERR_INVALID, "phase counters not enabled");
+  std::vector<long long> h(n);
+  CU(cudaMemcpy(h.data(), c->d_phase, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  for (size_t i = 0; i < n; i++) out[i % 8] += h[i];
+  CU(cudaFree(c->d_phase));
+  c->d_phase = nullptr;
+  return 0;
+}
 extern "C" int fheram_host_register(void* p, size_t bytes) {
   CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
   return 0;
@@ -410,6 +432,7 @@ static VmpArgs base_args(fheram_ctx* c, int n_items, const int* src, int* dst, l
   a.scratch = (int*)c->scratch.p;
   a.sign = 1;
   a.tw = c->tw;
+  a.phase_cycles = c->d_phase;
   return a;
 }
 static size_t prof_event(fheram_ctx* c) {

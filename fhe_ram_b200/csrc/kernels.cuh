@@ -198,19 +198,24 @@ __device__ __forceinline__ void inv_transform(double2 (&x)[8], double2* work, in
 
 // ---- integer helpers (balanced base-2^17 digits) -------------------------------------
 __device__ __forceinline__ long long sext17(long long x) { return (x << 47) >> 47; }
+__device__ __forceinline__ int sext17i(int x) {
+  int r;
+  asm("bfe.s32 %0, %1, 0, 17;" : "=r"(r) : "r"(x));
+  return r;
+}
 
-// ceil(X/2) of the 3-limb integer X = a0 2^34 + a1 2^17 + a2 in balanced digits: this is what
-// Poulpy's vec_znx_rsh_inplace(k = 1) produces (see oracle vz_rsh_inplace).
+// Poulpy's vec_znx_rsh_inplace(k = 1) on a 3-limb coefficient, step by step in 32-bit
+// arithmetic (oracle vz_rsh_inplace: shift by one limb, left-shift by 16 inside the
+// normalisation): equals the balanced digits of ceil(X/2), X = a0 2^34 + a1 2^17 + a2.
 __device__ __forceinline__ void rsh1_3(int a0, int a1, int a2, int& d0, int& d1, int& d2) {
-  long long X = ((long long)a0 << 34) + ((long long)a1 << 17) + (long long)a2;
-  long long Y = (X + 1) >> 1;
-  long long t = sext17(Y);
-  d2 = (int)t;
-  Y = (Y - t) >> 17;
-  t = sext17(Y);
-  d1 = (int)t;
-  Y = (Y - t) >> 17;
-  d0 = (int)sext17(Y);
+  int carry = (a2 + 1) >> 1;                 // limb shifted out: carry only (digit -(a2&1) dropped)
+  int dpc = (-(a1 & 1) << 16) + carry;       // low bit of limb 1 lands on top of limb 2
+  d2 = sext17i(dpc);
+  carry = ((a1 + 1) >> 1) + ((dpc - d2) >> 17);
+  dpc = (-(a0 & 1) << 16) + carry;
+  d1 = sext17i(dpc);
+  carry = ((a0 + 1) >> 1) + ((dpc - d1) >> 17);
+  d0 = sext17i(carry);
 }
 
 // automorphism X -> X^g on coefficient index i: returns destination index, sets neg
@@ -262,7 +267,18 @@ struct VmpArgs {
   int rot_mul;
   int rot_const;           // added rotation (mod 2N), e.g. COMBINE2's t
   Twiddles tw;
+  // optional per-phase cycle counters (debug / DESIGN.md phase breakdown): gridDim.x * 8 slots
+  // 0 prologue, 1 forward pass 1, 2 forward warp passes, 3 contraction, 4 inverse, 5 epilogue, 6 rest
+  long long* phase_cycles;
 };
+#define PHASE_TICK(ph)                                                      \
+  do {                                                                      \
+    if (A.phase_cycles && threadIdx.x == 0) {                               \
+      const long long now_ = clock64();                                     \
+      A.phase_cycles[(size_t)blockIdx.x * 8 + (ph)] += now_ - phase_t0;     \
+      phase_t0 = now_;                                                      \
+    }                                                                       \
+  } while (0)
 
 // ======================================================================================
 // The fused kernel.
@@ -285,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
   // layout of a ciphertext buffer: [limb][col][N]
   auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
 
+  long long phase_t0 = A.phase_cycles ? clock64() : 0;
   for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
     int* dst = A.dst + (size_t)item * A.ct_stride;
     int* scr0 = A.scratch ? A.scratch + (size_t)blockIdx.x * 2 * A.ct_stride : nullptr;
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
         int rk = A.rot_const;
         if (A.rot_mod > 0) rk += A.rot_mul * (item % A.rot_mod);
         rk &= (2 * kN - 1);
-#pragma unroll 2
+#pragma unroll 4
         for (int m = 0; m < 16; m++) {
           const int i = T + 256 * m;  // 16 positions per thread: i and i + 2048 for m < 8
 #pragma unroll
@@ -337,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
         const int* a = src;
         const int* b = src + A.ct_stride;
         const int tt = A.rot_const;  // t
-#pragma unroll 2
+#pragma unroll 4
         for (int m = 0; m < 16; m++) {
           const int i = T + 256 * m;
           bool neg;
@@ -355,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
           }
         }
       }
+      PHASE_TICK(0);
       // input of the transforms
       const int* xin = (MODE == MODE_TRACE || MODE == MODE_COMBINE2) ? xb
                        : (MODE == MODE_EXT && step > 0) ? dst : src;
@@ -375,95 +393,109 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
         fwd_pass1_store(x, spectra + (size_t)rho * kM, T);
       }
       __syncthreads();
+      PHASE_TICK(1);
 #pragma unroll 1
       for (int rho = 0; rho < R * CIN; rho++) fwd_warp_passes(spectra + (size_t)rho * kM, w, lane, tw);
+      PHASE_TICK(2);
       // no barrier needed: the contraction reads only what this thread wrote
 
       // --------------- contraction + inverse transform + epilogue ------------------
+      // Both output columns of limb l are contracted together (each input spectrum value read
+      // from shared memory once for two outputs); carries fit 32 bits (|big| < 2^47).
+      int carryA[16], carryB[16];    // running carry of column 0 / column 1
+      int carry2A[16], carry2B[16];  // COMBINE2: carry of the second normalisation
+#pragma unroll
+      for (int q = 0; q < 16; q++) { carryA[q] = 0; carryB[q] = 0; carry2A[q] = 0; carry2B[q] = 0; }
 #pragma unroll 1
-      for (int co = 0; co < 2; co++) {
-        long long carry[16];
-        long long carry2[16];  // COMBINE2 second chain
+      for (int l = LOUT - 1; l >= 0; l--) {
+        double2 cur[8], nxt[8];
 #pragma unroll
-        for (int q = 0; q < 16; q++) { carry[q] = 0; carry2[q] = 0; }
-#pragma unroll 1
-        for (int l = LOUT - 1; l >= 0; l--) {
-          const int o = co * LOUT + l;
-          double2 acc[8];
+        for (int j = 0; j < 8; j++) { cur[j] = make_double2(0.0, 0.0); nxt[j] = make_double2(0.0, 0.0); }
+        const int P0 = 256 * w + lane;
+#pragma unroll(R * CIN <= 4 ? R * CIN : 2)
+        for (int rho = 0; rho < R * CIN; rho++) {
+          const double2* gp = G + ((size_t)rho * NOUT + l) * kM + P0;
+          const double2* ap = spectra + (size_t)rho * kM + P0;
+          double2 g0[8], g1[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc[j] = make_double2(0.0, 0.0);
-          const int P0 = 256 * w + lane;
-#pragma unroll 2
-          for (int rho = 0; rho < R * CIN; rho++) {
-            const double2* gp = G + ((size_t)rho * NOUT + o) * kM + P0;
-            const double2* ap = spectra + (size_t)rho * kM + P0;
-            double2 gv[8];
+          for (int j = 0; j < 8; j++) { g0[j] = __ldg(gp + 32 * j); g1[j] = __ldg(gp + (size_t)LOUT * kM + 32 * j); }
 #pragma unroll
-            for (int j = 0; j < 8; j++) gv[j] = __ldg(gp + 32 * j);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const double2 a = ap[32 * j];
-              acc[j].x = fma(a.x, gv[j].x, fma(-a.y, gv[j].y, acc[j].x));
-              acc[j].y = fma(a.x, gv[j].y, fma(a.y, gv[j].x, acc[j].y));
-            }
+          for (int j = 0; j < 8; j++) {
+            const double2 a = ap[32 * j];
+            cur[j].x = fma(a.x, g0[j].x, fma(-a.y, g0[j].y, cur[j].x));
+            cur[j].y = fma(a.x, g0[j].y, fma(a.y, g0[j].x, cur[j].y));
+            nxt[j].x = fma(a.x, g1[j].x, fma(-a.y, g1[j].y, nxt[j].x));
+            nxt[j].y = fma(a.x, g1[j].y, fma(a.y, g1[j].x, nxt[j].y));
           }
-          // operands gathered between the two barriers of the inverse transform
-          int xnat[16];  // small value added at the natural position (body add / expand)
-          int xpi[16];   // small value at the destination position
-          int dpos[16];  // destination index (after automorphism), bit 31 = negate
-          inv_transform(acc, work, T, w, lane, tw, [&]() {
+        }
+        PHASE_TICK(3);
+#pragma unroll 1
+        for (int co = 0; co < 2; co++) {
+          const bool has_small = l < R;  // the small operand has R limbs
+          int xnat[16];  // MODE_TRACE body limb at the natural position: must be read before any
+                         // thread overwrites it in place, i.e. between the two barriers
+          inv_transform(cur, work, T, w, lane, tw, [&]() {
+            if (MODE == MODE_TRACE) {
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
-              const int i = T + 256 * (q & 7) + (q >> 3) * kM;
-              xnat[q] = 0; xpi[q] = 0; dpos[q] = i;
-              if (MODE == MODE_EXT) continue;
-              const bool has_small = l < R;  // small operand has R limbs
-              if (MODE == MODE_EXPAND) {
-                if (co == 1 && has_small) xnat[q] = xin[CT(0, l) + i];
-                continue;
+              for (int q = 0; q < 16; q++) {
+                const int i = T + 256 * (q & 7) + (q >> 3) * kM;
+                xnat[q] = (co == 0 && has_small) ? xb[CT(0, l) + i] : 0;
               }
-              if (co == 0 && has_small) xnat[q] = xin[CT(0, l) + i];
-              bool neg;
-              const int d = auto_index(i, g, neg);
-              dpos[q] = d | (neg ? 0x80000000 : 0);
-              if (MODE == MODE_TRACE && has_small) xpi[q] = xb[CT(co, l) + d];
-              if (MODE == MODE_COMBINE2 && l < LRES) xpi[q] = scr1[CT(co, l) + d];
             }
           });
-          // acc[m] = M * z[T + 256 m]
+          PHASE_TICK(4);
+          // cur[m] = M * z[T + 256 m]
 #pragma unroll
           for (int q = 0; q < 16; q++) {
-            const double v = (q < 8) ? acc[q & 7].x : acc[q & 7].y;
-            long long big = __double2ll_rn(v * kInvM) + (long long)xnat[q];
-            const int d = dpos[q] & 0x7fffffff;
-            const bool neg = dpos[q] < 0;
+            const int i = T + 256 * (q & 7) + (q >> 3) * kM;
+            const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
+            long long big = __double2ll_rn(v * kInvM);
+            int d = i;
+            bool neg = false;
+            if (MODE == MODE_TRACE) {
+              big += (long long)xnat[q];
+            } else if (MODE == MODE_EXPAND) {
+              if (co == 1 && has_small) big += (long long)xin[CT(0, l) + i];
+            } else if (MODE != MODE_EXT) {
+              if (co == 0 && has_small) big += (long long)xin[CT(0, l) + i];
+            }
+            if (MODE == MODE_TRACE || MODE == MODE_COMBINE2 || MODE == MODE_AUTO) d = auto_index(i, g, neg);
             if (MODE == MODE_TRACE) {
               // automorphism on the big value, +/- it, add the small input, one normalisation
-              if (neg) big = -big;
-              if (A.sign < 0) big = -big;
-              big += (long long)xpi[q];
+              if (neg != (A.sign < 0)) big = -big;
+              if (has_small) big += (long long)xb[CT(co, l) + d];
             }
-            const long long t = big + carry[q];
-            const long long dg = sext17(t);
-            carry[q] = (t - dg) >> kK;
+            const long long t = big + (long long)carryA[q];
+            const int c = (int)((t + 65536) >> kK);
+            const int dg = (int)t - (c << kK);
+            carryA[q] = c;
             if (l < LRES) {
               if (MODE == MODE_EXT || MODE == MODE_EXPAND) {
-                dst[CT(co, l) + d] = (int)dg;
+                dst[CT(co, l) + d] = dg;
               } else if (MODE == MODE_AUTO) {
-                dst[CT(co, l) + d] = neg ? -(int)dg : (int)dg;
+                dst[CT(co, l) + d] = neg ? -dg : dg;
               } else if (MODE == MODE_TRACE) {
-                xb[CT(co, l) + d] = (int)dg;
+                xb[CT(co, l) + d] = dg;
               } else if (MODE == MODE_COMBINE2) {
                 // y = phi(normalize(KS(D))) digit at d; a' = normalize(S - y); out = a' X^t
-                const long long y = neg ? -dg : dg;
-                const long long t2 = (long long)xpi[q] - y + carry2[q];
-                const long long dg2 = sext17(t2);
-                carry2[q] = (t2 - dg2) >> kK;
+                const int y = neg ? -dg : dg;
+                const int t2 = scr1[CT(co, l) + d] - y + carry2A[q];
+                const int dg2 = sext17i(t2);
+                carry2A[q] = (t2 - dg2) >> kK;
                 bool rneg;
                 const int dd = rot_index(d, A.rot_const, rneg);  // a' * X^t
-                dst[CT(co, l) + dd] = rneg ? -(int)dg2 : (int)dg2;
+                dst[CT(co, l) + dd] = rneg ? -dg2 : dg2;
               }
             }
+          }
+          PHASE_TICK(5);
+          // rotate the per-column state so the loop body always works on (cur, carryA, carry2A)
+#pragma unroll
+          for (int j = 0; j < 8; j++) { const double2 t = cur[j]; cur[j] = nxt[j]; nxt[j] = t; }
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            int t = carryA[q]; carryA[q] = carryB[q]; carryB[q] = t;
+            if (MODE == MODE_COMBINE2) { t = carry2A[q]; carry2A[q] = carry2B[q]; carry2B[q] = t; }
           }
         }
       }
@@ -475,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
       for (int i = T; i < 2 * R * kN; i += kThreads) dst[i] = xb[i];
     }
     __syncthreads();  // xb / spectra reuse by the next item
+    PHASE_TICK(6);
   }
 }
 

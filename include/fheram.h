@@ -90,6 +90,10 @@ int fheram_ctx_profile(fheram_ctx *ctx, int enable);
 int fheram_ctx_profile_get(fheram_ctx *ctx, double ms[4], uint64_t launches[4], uint64_t ops[4]);
 /* FP64 FMA peak of the device in TFLOP/s (dependent-chain DFMA probe, best of reps) */
 int fheram_fp64_peak_probe(fheram_ctx *ctx, int reps, double *tflops);
+/* debug: per-phase SM-cycle counters of the fused kernels, summed over CTAs.  enable = 1 starts
+ * counting, enable = 0 reads {prologue, forward pass 1, forward warp passes, contraction, inverse
+ * transform, epilogue, rest, -} into out and stops. */
+int fheram_debug_phase_cycles(fheram_ctx *ctx, int enable, long long out[8]);
 /* pin / unpin a caller-owned host buffer (cudaHostRegister) so uploads run at PCIe speed */
 int fheram_host_register(void *p, size_t bytes);
 int fheram_host_unregister(void *p);
