@@ -243,10 +243,8 @@ def main():
             return ram.read_batch_device(addr_res, keys)
 
         def run_e2e():
-            a = fr.Address.from_limbs(params, addr_limbs, B)   # host int64 limbs -> device + prepare
-            api._check(api.lib().fheram_ram_read_batch(ram.h, a.device(), keys.h, api._p(out_host)))
-            a.close()
-            return out_host
+            # host int64 address limbs -> device, prepare, read, int64 results back on the host
+            return ram.read_batch_host(addr_limbs, B, keys, out_host)
 
         def check(out):
             for b in (0, B // 2, B - 1):

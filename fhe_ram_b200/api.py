@@ -92,6 +92,7 @@ SIGNATURES = {
     "fheram_ram_read_prepare_write": (C.c_int, [_V, _V, _V, _P64]),
     "fheram_ram_write": (C.c_int, [_V, _P64, _V, _V]),
     "fheram_ram_read_batch": (C.c_int, [_V, _V, _V, _P64]),
+    "fheram_ram_read_batch_host": (C.c_int, [_V, _P64, C.c_int, _V, _P64]),
     "fheram_ram_read_batch_device": (C.c_int, [_V, _V, _V, _PV]),
     "fheram_download_glwe": (C.c_int, [_V, _V, C.c_int, _P64]),
     "fheram_ram_read_local_device": (C.c_int, [_V, _V, _V, _PV]),
@@ -474,6 +475,13 @@ class Ram:
         """n independent reads (BASELINE.json config 3): [n][word_size] GLWE."""
         out = self._out(addresses.count)
         _check(lib().fheram_ram_read_batch(self.h, addresses.device(), keys.h, _p(out)))
+        return out
+
+    def read_batch_host(self, addr_limbs: np.ndarray, n: int, keys: EvaluationKeysPrepared, out=None) -> np.ndarray:
+        """n reads straight from host int64 address limbs (pipelined upload / prepare / read / download)."""
+        out = self._out(n) if out is None else out
+        _check(lib().fheram_ram_read_batch_host(self.h, _p(np.ascontiguousarray(addr_limbs, dtype=np.int64).reshape(-1)),
+                                                n, keys.h, _p(out.reshape(-1))))
         return out
 
     def read_batch_device(self, addresses: Address, keys: EvaluationKeysPrepared) -> int:

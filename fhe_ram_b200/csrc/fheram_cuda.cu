@@ -892,6 +892,97 @@ extern "C" int fheram_ram_read(fheram_ram* r, const fheram_address* addr, const 
   return fheram_ram_read_batch(r, addr, k, out);
 }
 
+// Pipelined end-to-end batched read from HOST buffers (the reference-facing call for a batch):
+// addresses arrive as int64 limbs in host memory, results leave as int64 limbs.  Chunks of
+// addresses are double-buffered: the H2D copy of chunk k+1 runs on a copy stream while chunk k is
+// converted, prepared (CoordinatePrepared::prepare) and read on the compute stream.
+extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_host, int n,
+                                          const fheram_keys* k, int64_t* out_host) {
+  if (!r || !ggsw_host || !k || !out_host || n < 1) return fail(FHERAM_ERR_INVALID, "bad argument");
+  if (k->c != r->c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
+  if (!r->loaded) return fail(FHERAM_ERR_UNINIT, "unitialized memory: self.data.len()=0 (src/ram.rs:182-185)");
+  if (r->state) return fail(FHERAM_ERR_STATE, "invalid call to Memory.read: internal state is true (src/ram.rs:393-396)");
+  if (r->n_shards != 1) return fail(FHERAM_ERR_INVALID, "sharded RAM: use the *_device entry points");
+  fheram_ctx* c = r->c;
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  const int ws = c->params.word_size;
+  const long L = c->ct_stride();
+  const size_t per_addr = (size_t)d.n_ggsw * c->ggsw_raw_len();  // limbs per address
+  int chunk = batch_chunk(r);
+  if (chunk > 32) chunk = 32;
+  if (chunk > n) chunk = n;
+  struct Set { long long* stage = nullptr; fheram_address a; cudaEvent_t copied, freed; };
+  Set sets[2];
+  cudaStream_t copy_stream;
+  CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  long long* out_stage = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(copy_stream);
+    cudaStreamSynchronize(c->stream);
+    for (auto& s : sets) {
+      cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
+      s.a.raw = nullptr; s.a.prep = nullptr;
+      if (s.copied) cudaEventDestroy(s.copied);
+      if (s.freed) cudaEventDestroy(s.freed);
+    }
+    cudaFree(out_stage);
+    cudaStreamDestroy(copy_stream);
+  };
+#define TRYC(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+#define CUC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  for (auto& s : sets) {
+    s.a.c = c; s.a.count = chunk;
+    s.copied = nullptr; s.freed = nullptr;
+    CUC(cudaMalloc(&s.stage, sizeof(long long) * chunk * per_addr));
+    CUC(cudaMalloc(&s.a.raw, sizeof(int) * chunk * per_addr));
+    CUC(cudaMalloc(&s.a.prep, sizeof(double2) * (size_t)chunk * d.n_ggsw * c->ggsw_prep_len()));
+    CUC(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming));
+  }
+  CUC(cudaMalloc(&out_stage, sizeof(long long) * (size_t)chunk * ws * L));
+  const int n_chunks = (n + chunk - 1) / chunk;
+  auto issue_copy = [&](int ci) -> int {
+    Set& s = sets[ci & 1];
+    const int b0 = ci * chunk, nb = n - b0 < chunk ? n - b0 : chunk;
+    if (ci >= 2) CU(cudaStreamWaitEvent(copy_stream, s.freed, 0));
+    CU(cudaMemcpyAsync(s.stage, ggsw_host + (size_t)b0 * per_addr, sizeof(long long) * nb * per_addr,
+                       cudaMemcpyHostToDevice, copy_stream));
+    CU(cudaEventRecord(s.copied, copy_stream));
+    return 0;
+  };
+  TRYC(issue_copy(0));
+  for (int ci = 0; ci < n_chunks; ci++) {
+    if (ci + 1 < n_chunks) TRYC(issue_copy(ci + 1));
+    Set& s = sets[ci & 1];
+    const int b0 = ci * chunk, nb = n - b0 < chunk ? n - b0 : chunk;
+    s.a.count = nb;
+    CUC(cudaStreamWaitEvent(c->stream, s.copied, 0));
+    k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
+    c->launches++;
+    TRYC(prepare(c, s.a.raw, c->ggsw_raw_len(), s.a.prep, c->ggsw_prep_len(), nb * d.n_ggsw, d.dnum_ct, 2, d.size_addr));
+    TRYC(ram_local_stage(r, &s.a, 0, nb, k, false));
+    TRYC(ram_finish_stage(r, (const int*)r->partial.p, nb, 0, nb, &s.a, 0, k, false));
+    CUC(cudaEventRecord(s.freed, c->stream));
+    k_i32_to_i64<<<c->sm_count * 4, 256, 0, c->stream>>>((const int*)r->result.p, out_stage, (size_t)nb * ws * L);
+    c->launches++;
+    CUC(cudaMemcpyAsync(out_host + (size_t)b0 * ws * L, out_stage, sizeof(long long) * (size_t)nb * ws * L,
+                        cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUC(cudaStreamSynchronize(c->stream));
+  int err = 0;
+  CUC(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  cleanup();
+#undef TRYC
+#undef CUC
+  if (err) {
+    cudaMemset(c->d_err, 0, sizeof(int));
+    return fail(FHERAM_ERR_RANGE, "limb outside +-2^30: ciphertext limbs must be (nearly) normalised");
+  }
+  return 0;
+}
+
 extern "C" int fheram_ram_read_local_device(fheram_ram* r, const fheram_address* addr,
                                             const fheram_keys* k, const int32_t** d_partial) {
   TRY(check_read_args(r, addr, k));

@@ -141,6 +141,12 @@ int fheram_ram_write(fheram_ram *r, const int64_t *w, const fheram_address *addr
  * addresses (fheram_address_load_batch); out = [n][word_size] GLWE */
 int fheram_ram_read_batch(fheram_ram *r, const fheram_address *addr, const fheram_keys *k,
                           int64_t *out);
+/* same, straight from HOST buffers (the reference-facing batch call): ggsw = n addresses as int64
+ * limbs (pinned memory recommended, fheram_host_register), out = [n][word_size] GLWE.  Upload,
+ * on-device prepare, read and download are pipelined in chunks (copy of chunk k+1 overlaps the
+ * reads of chunk k). */
+int fheram_ram_read_batch_host(fheram_ram *r, const int64_t *ggsw, int n, const fheram_keys *k,
+                               int64_t *out);
 /* device-resident variant: result left in the RAM's result arena (int32 device limbs,
  * [n][word_size][limb][col][N]); returns the device pointer.  No host copies. */
 int fheram_ram_read_batch_device(fheram_ram *r, const fheram_address *addr, const fheram_keys *k,

@@ -173,6 +173,28 @@ def test_batched_reads_equal_single_reads(scenario, gpu_keys):
     ram.close()
 
 
+def test_host_buffer_batch_pipeline(scenario, gpu_keys):
+    """fheram_ram_read_batch_host (chunked, double-buffered) == one read per address."""
+    s = scenario(1 << 13, 2)
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    idxs = [(37 * i + 11) % p.max_addr() for i in range(70)]      # > 2 chunks of 32
+    addrs = [s.address(i) for i in idxs]
+    limbs = np.stack([a.data for a in addrs])
+    got = ram.read_batch_host(limbs, len(idxs), keys)
+    for b in (0, 1, 31, 32, 63, 64, 69):
+        assert np.array_equal(got[b], ram.read(addrs[b], keys)), b
+        s.check_decrypt(got[b], idxs[b])
+    bad = limbs.copy()
+    bad[3, 5] = 1 << 40
+    with pytest.raises(fr.FheRamError) as e:
+        ram.read_batch_host(bad, len(idxs), keys)
+    assert e.value.code == -6
+    ram.close()
+
+
 def test_state_machine_and_errors(scenario, gpu_keys):
     """assert!s of src/ram.rs:182-185,243,393-396,555-558 become error codes."""
     s = scenario()
