@@ -431,6 +431,7 @@ static VmpArgs base_args(fheram_ctx* c, int n_items, const int* src, int* dst, l
   a.ct_stride = ct_stride;
   a.scratch = (int*)c->scratch.p;
   a.sign = 1;
+  for (int i = 0; i < kMaxSteps; i++) { a.gal[i] = 1; a.gal_inv[i] = 1; }
   a.tw = c->tw;
   a.phase_cycles = c->d_phase;
   return a;
@@ -462,11 +463,18 @@ static int launch(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem, int cl
 }
 
 // vmp_prepare of n_mat matrices
+static int inv_mod_2n(int g) {  // g odd, modulus 2N = 8192: g^(N-1) since the unit group has exponent N
+  long r = 1, b = ((g % (2 * kN)) + 2 * kN) % (2 * kN);
+  for (int e = kN - 1; e; e >>= 1) { if (e & 1) r = r * b % (2 * kN); b = b * b % (2 * kN); }
+  return (int)r;
+}
+// vmp_prepare of n_mat matrices; gal != 1 prepares phi_gal(matrix) (key-switch keys, see k_vmp)
 static int prepare(fheram_ctx* c, const int* raw, long raw_stride, double2* out, long out_stride,
-                   int n_mat, int rows, int cin, int lout) {
+                   int n_mat, int rows, int cin, int lout, int gal = 1) {
   PrepArgs a;
   a.raw = raw; a.out = out; a.raw_stride = raw_stride; a.out_stride = out_stride;
   a.rows = rows; a.cin = cin; a.lout = lout; a.tw = c->tw;
+  a.gal_inv = inv_mod_2n(gal);
   int grid = n_mat * rows * cin * 2 * lout;
   k_prepare<<<grid, kThreads, 0, c->stream>>>(a);
   c->launches++;
@@ -499,10 +507,15 @@ extern "C" int fheram_keys_prepare(fheram_ctx* c, const int64_t* atk_glwe, const
   CU(cudaMalloc(&k->atk_inv, sizeof(double2) * c->evk_inv_prep_len()));
   CU(cudaMalloc(&k->tsk, sizeof(double2) * c->evk_inv_prep_len()));
   TRY(upload_i64(c, atk_glwe, atk_raw * d.log_n, tmp));
-  TRY(prepare(c, tmp, (long)atk_raw, k->atk, c->atk_prep_len(), d.log_n, d.dnum_ct, 1, d.size_evk_trace));
+  // trace key i is stored as phi_{g_i}(key): the kernels transform phi_g(x) and get phi_g(KS(x))
+  for (int i = 0; i < d.log_n; i++)
+    TRY(prepare(c, tmp + (size_t)i * atk_raw, (long)atk_raw, k->atk + (size_t)i * c->atk_prep_len(),
+                c->atk_prep_len(), 1, d.dnum_ct, 1, d.size_evk_trace,
+                (int)((galois(d.log_n, i) + 2 * kN) % (2 * kN))));
   CU(cudaStreamSynchronize(c->stream));
   TRY(upload_i64(c, atk_inv, inv_raw, tmp));
-  TRY(prepare(c, tmp, (long)inv_raw, k->atk_inv, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv));
+  TRY(prepare(c, tmp, (long)inv_raw, k->atk_inv, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv,
+              2 * kN - 1));
   CU(cudaStreamSynchronize(c->stream));
   TRY(upload_i64(c, tsk, inv_raw, tmp));
   TRY(prepare(c, tmp, (long)inv_raw, k->tsk, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv));
@@ -585,6 +598,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   for (int s = 0; s < a.n_steps; s++) {
     a.mat[s] = k->atk + (size_t)(g0 + s) * c->atk_prep_len();
     a.gal[s] = (int)((galois(c->d.log_n, g0 + s) + 2 * kN) % (2 * kN));
+    a.gal_inv[s] = inv_mod_2n(a.gal[s]);
   }
   a.rot_mod = rot_mod; a.rot_mul = rot_mul; a.rot_const = rot_const; a.sign = sign;
   if (a.n_steps == 0) {
@@ -604,6 +618,7 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.n_steps = 1;
   a.mat[0] = k->atk + (size_t)level * c->atk_prep_len();
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
+  a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
   return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }
@@ -1049,6 +1064,7 @@ static int ggsw_invert_device(fheram_ctx* c, const fheram_keys* k, const int* ra
     a.n_steps = 1;
     a.mat[0] = k->atk_inv;
     a.gal[0] = 2 * kN - 1;
+    a.gal_inv[0] = 2 * kN - 1;
     TRY(launch(c, K_AUTO_INV, a, smem_bytes(4, 1, false)));
   }
   {
@@ -1056,6 +1072,7 @@ static int ggsw_invert_device(fheram_ctx* c, const fheram_keys* k, const int* ra
     a.n_steps = 1;
     a.mat[0] = k->tsk;
     a.gal[0] = 1;
+    a.gal_inv[0] = 1;
     TRY(launch(c, K_EXPAND, a, smem_bytes(4, 1, false)));
   }
   return 0;
@@ -1206,6 +1223,7 @@ extern "C" int fheram_glwe_automorphism(fheram_ctx* c, const fheram_keys* k, int
     a.n_steps = 1;
     a.mat[0] = k->atk + (size_t)gal_idx * c->atk_prep_len();
     a.gal[0] = (int)((galois(c->d.log_n, gal_idx) + 2 * kN) % (2 * kN));
+    a.gal_inv[0] = inv_mod_2n(a.gal[0]);
     TRY(launch(c, K_AUTO3, a, smem_bytes(3, 1, false)));
     res = (int*)c->opbuf[1].p;
   } else {

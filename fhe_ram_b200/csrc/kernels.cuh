@@ -47,6 +47,12 @@ struct Twiddles {
 // zeta(s,b) for s < 6 at index (1<<s)+b  (1 KiB, uniform / warp-uniform accesses only)
 __constant__ double2 c_tw_lo[64];
 
+// read-only 16-byte global load that the compiler may not sink past barriers (prefetch slots)
+__device__ __forceinline__ double2 ldg_pinned(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ double2 mul_i(double2 w) { return make_double2(-w.y, w.x); }
 __device__ __forceinline__ double2 conj_(double2 w) { return make_double2(w.x, -w.y); }
 
@@ -258,7 +264,8 @@ struct VmpArgs {
   long ct_stride;    // ints per ciphertext
   // matrices: step s of item -> mat[s] + (item / mat_div) * mat_stride   (mat_div 0: shared)
   const double2* mat[kMaxSteps];
-  int gal[kMaxSteps];      // automorphism exponent (mod 2N, positive) per step
+  int gal[kMaxSteps];      // automorphism exponent g (mod 2N, positive) per step
+  int gal_inv[kMaxSteps];  // g^-1 mod 2N: phi_g(x)[j] = +/- x[j * g^-1 mod 2N]
   int mat_div;
   long mat_stride;         // in double2
   int n_steps;
@@ -282,6 +289,11 @@ struct VmpArgs {
 
 // ======================================================================================
 // The fused kernel.
+// Key-switch modes use keys prepared as phi_g(K) (k_prepare with gal_inv): since
+// phi_g(sum_r a_r * K_r) = sum_r phi_g(a_r) * phi_g(K_r), transforming phi_g(x) instead of x makes
+// the inverse transform deliver phi_g(KS(x)) directly in natural coefficient order, so every
+// epilogue works on the thread's own positions (no scatter) and only reads of the small input
+// are gathered.
 //   R     limbs of the input ciphertext that are transformed (rows per input column)
 //   CIN   2: both columns enter the product (GGSW), 1: mask column only (key switch)
 //   LOUT  limbs of the matrix / big result;   LRES  limbs kept after normalisation
@@ -376,20 +388,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
       // input of the transforms
       const int* xin = (MODE == MODE_TRACE || MODE == MODE_COMBINE2) ? xb
                        : (MODE == MODE_EXT && step > 0) ? dst : src;
-      if (MODE == MODE_EXT && step > 0) __syncthreads();  // previous step's dst writes visible
+      constexpr bool PERM = (MODE == MODE_TRACE || MODE == MODE_COMBINE2 || MODE == MODE_AUTO);
+      const int ginv = A.gal_inv[step];
+      // the permuted loads below read positions other threads wrote in the prologue
+      if (MODE == MODE_TRACE || MODE == MODE_COMBINE2 || (MODE == MODE_EXT && step > 0)) __syncthreads();
 
       // --------------------------- forward transforms ------------------------------
-#pragma unroll 1
-      for (int rho = 0; rho < R * CIN; rho++) {
+      // integer limbs of row rho+1 are requested while row rho is converted and transformed
+      auto load_row = [&](int rho, int (&v)[16]) {
         const int limb = rho / CIN;
         const int col = CIN == 2 ? (rho % CIN) : 1;
         const int* p = xin + CT(col, limb);
-        double2 x[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
           const int i = T + 256 * m;
-          x[m] = make_double2((double)p[i], (double)p[i + kM]);
+          if (PERM) {
+            // phi_g(x)[i] and phi_g(x)[i + M]: (i + M) g^-1 = i g^-1 + M (g^-1 mod 4)  (mod 2N)
+            const int u = (i * ginv) & (2 * kN - 1);
+            const int u2 = (u + kM * (ginv & 3)) & (2 * kN - 1);
+            const int a = p[u & (kN - 1)], b = p[u2 & (kN - 1)];
+            v[m] = u >= kN ? -a : a;
+            v[m + 8] = u2 >= kN ? -b : b;
+          } else {
+            v[m] = p[i];
+            v[m + 8] = p[i + kM];
+          }
         }
+      };
+      int nx[16];
+      load_row(0, nx);
+#pragma unroll 1
+      for (int rho = 0; rho < R * CIN; rho++) {
+        double2 x[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) x[m] = make_double2((double)nx[m], (double)nx[m + 8]);
+        if (rho + 1 < R * CIN) load_row(rho + 1, nx);
         fwd_pass1_store(x, spectra + (size_t)rho * kM, T);
       }
       __syncthreads();
@@ -400,8 +433,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
       // no barrier needed: the contraction reads only what this thread wrote
 
       // --------------- contraction + inverse transform + epilogue ------------------
-      // Both output columns of limb l are contracted together (each input spectrum value read
+      // Both output columns of limb l are contracted together (each input spectrum value is read
       // from shared memory once for two outputs); carries fit 32 bits (|big| < 2^47).
+      // (A register prefetch of the next output's matrix rows across the inverse transform was
+      // measured and does not overlap: the L2 port runs at ~55 B/clk/SM either way.)
+      constexpr int NR = R * CIN;
+      const int P0 = 256 * w + lane;
       int carryA[16], carryB[16];    // running carry of column 0 / column 1
       int carry2A[16], carry2B[16];  // COMBINE2: carry of the second normalisation
 #pragma unroll
@@ -411,9 +448,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
         double2 cur[8], nxt[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) { cur[j] = make_double2(0.0, 0.0); nxt[j] = make_double2(0.0, 0.0); }
-        const int P0 = 256 * w + lane;
-#pragma unroll(R * CIN <= 4 ? R * CIN : 2)
-        for (int rho = 0; rho < R * CIN; rho++) {
+#pragma unroll(NR <= 4 ? NR : 2)
+        for (int rho = 0; rho < NR; rho++) {
           const double2* gp = G + ((size_t)rho * NOUT + l) * kM + P0;
           const double2* ap = spectra + (size_t)rho * kM + P0;
           double2 g0[8], g1[8];
@@ -432,38 +468,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
 #pragma unroll 1
         for (int co = 0; co < 2; co++) {
           const bool has_small = l < R;  // the small operand has R limbs
-          int xnat[16];  // MODE_TRACE body limb at the natural position: must be read before any
-                         // thread overwrites it in place, i.e. between the two barriers
+          int xnat[16];  // MODE_TRACE: phi_g(x) body limb; read before any thread overwrites the
+                         // buffer in place, i.e. between the two barriers of the inverse transform
           inv_transform(cur, work, T, w, lane, tw, [&]() {
             if (MODE == MODE_TRACE) {
 #pragma unroll
               for (int q = 0; q < 16; q++) {
                 const int i = T + 256 * (q & 7) + (q >> 3) * kM;
-                xnat[q] = (co == 0 && has_small) ? xb[CT(0, l) + i] : 0;
+                bool neg;
+                const int u = auto_index(i, ginv, neg);
+                const int v = (co == 0 && has_small) ? xb[CT(0, l) + u] : 0;
+                xnat[q] = neg ? -v : v;
               }
             }
           });
           PHASE_TICK(4);
-          // cur[m] = M * z[T + 256 m]
+          // cur[m] = M * phi_g(vmp)[T + 256 m] (natural order; plain vmp for EXT / EXPAND)
 #pragma unroll
           for (int q = 0; q < 16; q++) {
             const int i = T + 256 * (q & 7) + (q >> 3) * kM;
             const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
             long long big = __double2ll_rn(v * kInvM);
-            int d = i;
             bool neg = false;
             if (MODE == MODE_TRACE) {
+              // x +/- phi(KS(x)), KS(x) = vmp + body:  phi(body) gathered above
               big += (long long)xnat[q];
+              if (A.sign < 0) big = -big;
+              if (has_small) big += (long long)xb[CT(co, l) + i];
             } else if (MODE == MODE_EXPAND) {
               if (co == 1 && has_small) big += (long long)xin[CT(0, l) + i];
-            } else if (MODE != MODE_EXT) {
-              if (co == 0 && has_small) big += (long long)xin[CT(0, l) + i];
-            }
-            if (MODE == MODE_TRACE || MODE == MODE_COMBINE2 || MODE == MODE_AUTO) d = auto_index(i, g, neg);
-            if (MODE == MODE_TRACE) {
-              // automorphism on the big value, +/- it, add the small input, one normalisation
-              if (neg != (A.sign < 0)) big = -big;
-              if (has_small) big += (long long)xb[CT(co, l) + d];
+            } else if (MODE == MODE_AUTO || MODE == MODE_COMBINE2) {
+              // phi(normalize(KS(x))): run the carry chain in the pre-automorphism sign frame
+              const int u = auto_index(i, ginv, neg);
+              if (neg) big = -big;
+              if (co == 0 && has_small) big += (long long)xin[CT(0, l) + u];
             }
             const long long t = big + (long long)carryA[q];
             const int c = (int)((t + 65536) >> kK);
@@ -471,19 +509,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
             carryA[q] = c;
             if (l < LRES) {
               if (MODE == MODE_EXT || MODE == MODE_EXPAND) {
-                dst[CT(co, l) + d] = dg;
+                dst[CT(co, l) + i] = dg;
               } else if (MODE == MODE_AUTO) {
-                dst[CT(co, l) + d] = neg ? -dg : dg;
+                dst[CT(co, l) + i] = neg ? -dg : dg;
               } else if (MODE == MODE_TRACE) {
-                xb[CT(co, l) + d] = dg;
+                xb[CT(co, l) + i] = dg;
               } else if (MODE == MODE_COMBINE2) {
-                // y = phi(normalize(KS(D))) digit at d; a' = normalize(S - y); out = a' X^t
+                // y = phi(normalize(KS(D))); a' = normalize(S - y); out = a' X^t
                 const int y = neg ? -dg : dg;
-                const int t2 = scr1[CT(co, l) + d] - y + carry2A[q];
+                const int t2 = scr1[CT(co, l) + i] - y + carry2A[q];
                 const int dg2 = sext17i(t2);
                 carry2A[q] = (t2 - dg2) >> kK;
                 bool rneg;
-                const int dd = rot_index(d, A.rot_const, rneg);  // a' * X^t
+                const int dd = rot_index(i, A.rot_const, rneg);  // a' * X^t
                 dst[CT(co, l) + dd] = rneg ? -dg2 : dg2;
               }
             }
@@ -521,6 +559,7 @@ struct PrepArgs {
   double2* out;        // out_stride double2 apart
   long raw_stride, out_stride;
   int rows, cin, lout; // polys per matrix = rows*cin*2*lout
+  int gal_inv;         // 1: plain; else prepare phi_g(matrix) (g^-1 mod 2N), see k_vmp
   Twiddles tw;
 };
 __global__ void __launch_bounds__(kThreads, 2) k_prepare(const PrepArgs A) {
@@ -539,7 +578,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_prepare(const PrepArgs A) {
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     const int i = T + 256 * m;
-    x[m] = make_double2((double)p[i], (double)p[i + kM]);
+    const int u = (i * A.gal_inv) & (2 * kN - 1);
+    const int u2 = (u + kM * (A.gal_inv & 3)) & (2 * kN - 1);
+    const int v = p[u & (kN - 1)], v2 = p[u2 & (kN - 1)];
+    x[m] = make_double2((double)(u >= kN ? -v : v), (double)(u2 >= kN ? -v2 : v2));
   }
   fwd_pass1_store(x, spec, T);
   __syncthreads();
