@@ -320,6 +320,25 @@ def main():
                "h2d_bytes_per_step": int(addr_limbs.nbytes), "d2h_bytes_per_step": int(B * ws * L * 8),
                "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall / args.steps}
 
+    # ---- BASELINE config 4: interleaved read_prepare_write / write stream on the sharded RAM ----
+    pair_ms = None
+    if world > 1:
+        a1 = fr.Address.from_limbs(params, addr_limbs[0], 1)
+        wv = np.stack([fr.encrypt_glwe(params, int(v), sk) for v in (1, 2, 3, 4)[:ws]])
+        with torch.cuda.stream(stream):
+            sram.read_prepare_write(a1, keys)
+            sram.write(wv, a1, keys)
+            barrier()
+            t0 = time.perf_counter()
+            n_pairs = 5
+            for _ in range(n_pairs):
+                sram.read_prepare_write(a1, keys)
+                sram.write(wv, a1, keys)
+            barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_pairs], device=f"cuda:{device}")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        pair_ms = float(t.item())
+
     if rank != 0:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -354,6 +373,22 @@ def main():
             params.synchronize(); wr.append((time.perf_counter() - t0) * 1e3)
         lat["read_prepare_write_ms"] = float(np.median(rpw))
         lat["write_ms"] = float(np.median(wr))
+
+    # ---- BASELINE config 2: external-product microbenchmark (4096 GLWE x one prepared GGSW) ----
+    micro = None
+    if world == 1:
+        nb = 4096
+        rngm = np.random.default_rng(3)
+        g_in = rngm.integers(-(1 << 16), 1 << 16, size=(nb, params.glwe_len()), dtype=np.int64)
+        ggsw = rngm.integers(-(1 << 16), 1 << 16, size=params.ggsw_len(), dtype=np.int64)
+        api.external_product_batch(params, g_in[:296], ggsw)           # warm-up
+        params.profile(True)
+        api.external_product_batch(params, g_in, ggsw)
+        pm = params.profile_get()["ext"]
+        params.profile(False)
+        micro = {"workload": "4096 GLWE(k=51) x 1 prepared GGSW(k=68), N=4096", "kernel_ms": pm["ms"],
+                 "ext_products_per_s": nb / (pm["ms"] * 1e-3), "tflops": nb * F_EXT / (pm["ms"] * 1e-3) / 1e12,
+                 "gbs_algorithmic": nb * B_EXT / (pm["ms"] * 1e-3) / 1e9}
 
     # ---- roofline of the dominant kernel (CUDA events over the timed region) -------------
     (r_ext, r_ks), _ = op_model(max_addr, ws, params.base2d())
@@ -407,8 +442,10 @@ def main():
                    "l2": "inputs larger than L2: prepared addresses %.1f GiB + work arenas" % (B * params.n_ggsw() * 1.5 / 1024),
                    "address_gen_s": round(t_addr, 2)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu, **lat,
+        "cpu_baseline": cpu, "ext_product_microbench": micro, **lat,
     }
+    if pair_ms is not None:
+        line["sharded_rpw_write_pair_ms"] = pair_ms
     if "read_ms" in lat:
         line["vs_readme_read"] = 450.0 / lat["read_ms"]
         line["vs_readme_write"] = 1200.0 / lat["write_ms"]

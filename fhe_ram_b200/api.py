@@ -79,6 +79,10 @@ SIGNATURES = {
     "fheram_keys_destroy": (C.c_int, [_V]),
     "fheram_address_load": (C.c_int, [_V, _P64, _PV]),
     "fheram_address_load_batch": (C.c_int, [_V, _P64, C.c_int, _PV]),
+    "fheram_address_alloc": (C.c_int, [_V, C.c_int, _PV]),
+    "fheram_address_raw_ptr": (_V, [_V]),
+    "fheram_address_upload_slice": (C.c_int, [_V, _P64, C.c_int, C.c_int]),
+    "fheram_address_prepare": (C.c_int, [_V]),
     "fheram_address_count": (C.c_int, [_V]),
     "fheram_address_destroy": (C.c_int, [_V]),
     "fheram_ram_create": (C.c_int, [_V, _PV]),
@@ -373,6 +377,28 @@ class Address:
         a.count = count
         assert a.data.size == count * params.n_ggsw() * params.ggsw_len()
         return a
+
+    @classmethod
+    def device_alloc(cls, params: Parameters, count: int) -> "Address":
+        """n addresses allocated on the device only (multi-GPU path: upload_slice + all-gather into
+        raw_ptr() + prepare())."""
+        a = cls.__new__(cls)
+        a.params, a.data, a.count = params, None, count
+        h = C.c_void_p()
+        _check(lib().fheram_address_alloc(params.module(), count, C.byref(h)))
+        a.h = h
+        return a
+
+    def upload_slice(self, limbs: np.ndarray, first: int, count: int):
+        _check(lib().fheram_address_upload_slice(self.h, _p(np.ascontiguousarray(limbs, dtype=np.int64).reshape(-1)),
+                                                 first, count))
+
+    def raw_ptr(self) -> int:
+        return int(lib().fheram_address_raw_ptr(self.h))
+
+    def prepare(self):
+        _check(lib().fheram_address_prepare(self.h))
+        return self
 
     @classmethod
     def batch(cls, params: Parameters, addresses) -> "Address":

@@ -561,6 +561,34 @@ extern "C" int fheram_address_load_batch(fheram_ctx* c, const int64_t* ggsw, int
   *out = a;
   return 0;
 }
+// Multi-GPU upload path: allocate n addresses, fill slices of the raw limbs (host upload of this
+// rank's share, NVLink all-gather of the rest straight into fheram_address_raw_ptr), then prepare.
+extern "C" int fheram_address_alloc(fheram_ctx* c, int n, fheram_address** out) {
+  if (!c || !out || n < 1) return fail(FHERAM_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  fheram_address* a = new fheram_address();
+  a->c = c; a->count = n;
+  const size_t nm = (size_t)n * c->d.n_ggsw;
+  CU(cudaMalloc(&a->raw, sizeof(int) * nm * c->ggsw_raw_len()));
+  CU(cudaMalloc(&a->prep, sizeof(double2) * nm * c->ggsw_prep_len()));
+  *out = a;
+  return 0;
+}
+extern "C" int32_t* fheram_address_raw_ptr(fheram_address* a) { return a ? a->raw : nullptr; }
+extern "C" int fheram_address_upload_slice(fheram_address* a, const int64_t* ggsw, int first, int count) {
+  if (!a || !ggsw || first < 0 || count < 1 || first + count > a->count) return fail(FHERAM_ERR_INVALID, "bad slice");
+  fheram_ctx* c = a->c;
+  CU(cudaSetDevice(c->device));
+  const size_t per = (size_t)c->d.n_ggsw * c->ggsw_raw_len();
+  return upload_i64(c, ggsw, (size_t)count * per, a->raw + (size_t)first * per);
+}
+extern "C" int fheram_address_prepare(fheram_address* a) {  // CoordinatePrepared::prepare for every address
+  if (!a) return fail(FHERAM_ERR_INVALID, "null argument");
+  fheram_ctx* c = a->c;
+  CU(cudaSetDevice(c->device));
+  return prepare(c, a->raw, c->ggsw_raw_len(), a->prep, c->ggsw_prep_len(), a->count * c->d.n_ggsw, c->d.dnum_ct,
+                 2, c->d.size_addr);
+}
 extern "C" int fheram_address_load(fheram_ctx* c, const int64_t* ggsw, fheram_address** out) {
   return fheram_address_load_batch(c, ggsw, 1, out);
 }

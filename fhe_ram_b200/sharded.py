@@ -142,8 +142,20 @@ class ShardedRam:
         def run_resident():
             return self.read_batch_local_slice(resident, keys)
 
+        import torch
+        import torch.distributed as dist
+        G, rank = self.world, self.rank
+        per = params.n_ggsw() * params.ggsw_len()          # int32 limbs per address on the device
+
         def run_e2e():
-            a = api.Address.from_limbs(params, addr_limbs, B)
+            # every rank uploads only its own B/G addresses over PCIe; the others arrive over NVLink
+            a = api.Address.device_alloc(params, B)
+            cnt = B // G
+            a.upload_slice(addr_limbs[rank * cnt:(rank + 1) * cnt], rank * cnt, cnt)
+            if G > 1:
+                full = torch.as_tensor(_DevView(a.raw_ptr(), B * per), device=f"cuda:{params.device}")
+                dist.all_gather_into_tensor(full, full[rank * cnt * per:(rank + 1) * cnt * per])
+            a.prepare()
             mine = self.read_batch_local_slice(a, keys)
             n = mine.numel() // (params.word_size() * params.glwe_len()) * params.word_size()
             api._check(api.lib().fheram_download_glwe(params.module(), C.c_void_p(mine.data_ptr()), n,

@@ -113,6 +113,13 @@ typedef struct fheram_address fheram_address;
 int fheram_address_load(fheram_ctx *ctx, const int64_t *ggsw, fheram_address **out);
 /* n addresses at once, stored contiguously (batched reads) */
 int fheram_address_load_batch(fheram_ctx *ctx, const int64_t *ggsw, int n, fheram_address **out);
+/* multi-GPU upload path: allocate n addresses on the device, upload this rank's slice from the
+ * host, let the caller all-gather the other slices over NVLink straight into the raw int32 buffer
+ * (fheram_address_raw_ptr: [n][n_ggsw][ggsw_len] int32), then prepare all of them on the device */
+int fheram_address_alloc(fheram_ctx *ctx, int n, fheram_address **out);
+int32_t *fheram_address_raw_ptr(fheram_address *a);
+int fheram_address_upload_slice(fheram_address *a, const int64_t *ggsw, int first, int count);
+int fheram_address_prepare(fheram_address *a);
 int fheram_address_count(const fheram_address *a);
 int fheram_address_destroy(fheram_address *a);
 

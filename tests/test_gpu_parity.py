@@ -331,3 +331,39 @@ def test_cpp_host_layer_runs_the_example_scenario(built):
     r = subprocess.run([str(exe), "14"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "READ Elapsed time" in r.stdout and "WRITE Elapsed time" in r.stdout and r.stdout.strip().endswith("OK")
+
+
+def test_scaled_ram_2pow22_properties(scenario, gpu_keys):
+    """BASELINE.json config 5 size (2^22 entries; one byte lane to keep the oracle-free check fast):
+    coordinate 1 has four digits [3,3,3,1]; reads decrypt to the plaintext, write round trip."""
+    s = scenario(1 << 22, 1, 8)
+    fr, p = s.fr, s.params
+    assert p.base2d() == [[3, 3, 3, 3], [3, 3, 3, 1]] and p.n_glwe() == 1024
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    idxs = [0, (1 << 22) - 1, 4096 * 513 + 77, 1234567]
+    got = ram.read_batch(fr.Address.batch(p, [s.address(i) for i in idxs]), keys)
+    for b, i in enumerate(idxs):
+        s.check_decrypt(got[b], i)
+    a = s.address(3000001)
+    s.check_decrypt(ram.read_prepare_write(a, keys), 3000001)
+    ram.write(np.stack([fr.encrypt_glwe(p, 99, s.sk)]), a, keys)
+    d2 = s.data.copy()
+    d2[3000001] = 99
+    s.check_decrypt(ram.read(a, keys), 3000001, d2)
+    s.check_decrypt(ram.read(s.address(3000002), keys), 3000002, d2)
+    ram.close()
+
+
+def test_external_product_microbench_shape(scenario):
+    """BASELINE.json config 2 at reduced batch: n GLWE x one GGSW, random 17-bit limbs, bit-exact."""
+    from fhe_ram_b200 import api
+    s = scenario()
+    rng = np.random.default_rng(42)
+    n = 300          # > 2 waves of 148 CTAs
+    cts = _rand_glwe(rng, s.params, n)
+    ggsw = rng.integers(-(1 << 16), 1 << 16, size=s.params.ggsw_len(), dtype=np.int64)
+    got = api.external_product_batch(s.params, cts, ggsw)
+    for i in (0, 147, 148, 299):
+        assert np.array_equal(got[i], s.orc.external_product(cts[i], ggsw)), i
