@@ -13,6 +13,7 @@
 
 #include "../../include/fheram.h"
 #include "kernels.cuh"
+#include "kernels_ks2.cuh"
 
 using namespace fheram;
 
@@ -198,6 +199,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(K_AUTO3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, false)));
   CU(cudaFuncSetAttribute(K_AUTO_INV, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
   CU(cudaFuncSetAttribute(K_EXPAND, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
+  CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
+  CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   return 0;
 }
 
@@ -358,7 +361,7 @@ extern "C" int fheram_fp64_peak_probe(fheram_ctx* c, int reps, double* tflops) {
 extern "C" int fheram_debug_phase_cycles(fheram_ctx* c, int enable, long long out[8]) {
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
-  const size_t n = (size_t)c->sm_count * 8;
+  const size_t n = (size_t)c->sm_count * 2 * 8;
   if (enable) {
     if (!c->d_phase) CU(cudaMalloc(&c->d_phase, sizeof(long long) * n));
     CU(cudaMemset(c->d_phase, 0, sizeof(long long) * n));
@@ -462,6 +465,27 @@ static int launch(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem, int cl
   return 0;
 }
 
+// key-switch kernels built for two CTAs per SM (kernels_ks2.cuh); FHERAM_KS2=0 selects k_vmp
+static bool use_ks2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KS2"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename K>
+static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
+  if (a.n_items <= 0) return 0;
+  int grid = a.n_items < 2 * c->sm_count ? a.n_items : 2 * c->sm_count;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
+  kernel<<<grid, kThreads, kKs2Smem, c->stream>>>(a);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
 // vmp_prepare of n_mat matrices
 static int inv_mod_2n(int g) {  // g odd, modulus 2N = 8192: g^(N-1) since the unit group has exponent N
   long r = 1, b = ((g % (2 * kN)) + 2 * kN) % (2 * kN);
@@ -637,6 +661,9 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
+  // wide launches: two lean CTAs per SM overlap each other's phases; narrow ones (at most one
+  // item per SM) finish sooner with the single-CTA kernel
+  if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_TRACE>, a, KC_TRACE);
   return launch(c, K_TRACE, a, smem_bytes(3, 1, true), KC_TRACE);
 }
 // GLWEPacker::combine, both operands present, at tree level `level` (0-based absolute):
@@ -648,6 +675,7 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_COMBINE2>, a, KC_COMBINE2);
   return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }
 
