@@ -71,6 +71,8 @@ SIGNATURES = {
     "fheram_ctx_launch_count": (C.c_uint64, [_V]),
     "fheram_ctx_profile": (C.c_int, [_V, C.c_int]),
     "fheram_ctx_profile_get": (C.c_int, [_V, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fheram_ctx_profile_records": (C.c_int, [_V, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fheram_fp64_peak_probe": (C.c_int, [_V, C.c_int, C.POINTER(C.c_double)]),
     "fheram_debug_phase_cycles": (C.c_int, [_V, C.c_int, C.POINTER(C.c_longlong)]),
     "fheram_host_register": (C.c_int, [_V, C.c_size_t]),
@@ -241,6 +243,16 @@ class Parameters:
         _check(lib().fheram_ctx_profile_get(self.module(), ms, ln, ops))
         names = ("ext", "trace", "combine2", "other")
         return {n: {"ms": ms[i], "launches": int(ln[i]), "ops": int(ops[i])} for i, n in enumerate(names)}
+
+    def profile_records(self, max_n: int = 256):
+        """[(class, ms, items, steps)] per launch of the profiled region"""
+        cls = (C.c_int * max_n)()
+        ms = (C.c_double * max_n)()
+        it = (C.c_uint64 * max_n)()
+        st = (C.c_uint64 * max_n)()
+        n = lib().fheram_ctx_profile_records(self.module(), max_n, cls, ms, it, st)
+        names = ("ext", "trace", "combine2", "other")
+        return [(names[cls[i]], ms[i], int(it[i]), int(st[i])) for i in range(max(n, 0))]
 
     def fp64_peak_tflops(self, reps: int = 5) -> float:
         v = C.c_double()

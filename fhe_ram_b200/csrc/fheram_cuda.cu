@@ -318,6 +318,21 @@ extern "C" int fheram_ctx_profile_get(fheram_ctx* c, double ms[4], uint64_t laun
   return 0;
 }
 
+// per-launch records of the profiled region, in launch order; returns the number of records
+extern "C" int fheram_ctx_profile_records(fheram_ctx* c, int max_n, int* cls, double* ms, uint64_t* items,
+                                          uint64_t* steps) {
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+  int n = 0;
+  for (auto& r : c->ev_recs) {
+    if (n >= max_n) break;
+    float t = 0;
+    cudaEventElapsedTime(&t, c->ev_pool[r.e0], c->ev_pool[r.e1]);
+    cls[n] = r.cls; ms[n] = t; items[n] = r.items; steps[n] = r.steps;
+    n++;
+  }
+  return n;
+}
+
 __global__ void k_fp64_probe(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, b = 1e-7;

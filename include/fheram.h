@@ -88,6 +88,10 @@ uint64_t fheram_ctx_launch_count(const fheram_ctx *ctx);
  * 2 two-sided packer combine, 3 other.  ops = sum over launches of items x chain steps. */
 int fheram_ctx_profile(fheram_ctx *ctx, int enable);
 int fheram_ctx_profile_get(fheram_ctx *ctx, double ms[4], uint64_t launches[4], uint64_t ops[4]);
+/* per-launch records of the profiled region in launch order (class, device ms, items, chain
+ * steps); returns the number of records written (<= max_n) */
+int fheram_ctx_profile_records(fheram_ctx *ctx, int max_n, int *cls, double *ms, uint64_t *items,
+                               uint64_t *steps);
 /* FP64 FMA peak of the device in TFLOP/s (dependent-chain DFMA probe, best of reps) */
 int fheram_fp64_peak_probe(fheram_ctx *ctx, int reps, double *tflops);
 /* debug: per-phase SM-cycle counters of the fused kernels, summed over CTAs.  enable = 1 starts
