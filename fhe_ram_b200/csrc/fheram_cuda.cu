@@ -199,6 +199,7 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(K_AUTO3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, false)));
   CU(cudaFuncSetAttribute(K_AUTO_INV, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
   CU(cudaFuncSetAttribute(K_EXPAND, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
+  CU(cudaFuncSetAttribute(k_ext2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt2Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   return 0;
@@ -262,6 +263,7 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   for (int b = 0; b < 512; b++) zeta(9, b, q++);
   for (int b = 0; b < 512; b++) zeta(10, 2 * b, q++);
   CU(cudaMemcpyToSymbol(c_tw_lo, lo.data(), sizeof(double2) * 64));
+  CU(cudaMemcpyToSymbol(c_tw3, hi.data(), sizeof(double2) * 256));  // tw6 | tw7c | tw8c
   CU(cudaMalloc(&c->d_tw, sizeof(double2) * hi.size()));
   CU(cudaMemcpy(c->d_tw, hi.data(), sizeof(double2) * hi.size(), cudaMemcpyHostToDevice));
   c->tw.tw6 = c->d_tw;
@@ -487,12 +489,12 @@ static bool use_ks2() {
   return v == 1;
 }
 template <typename K>
-static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
+static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls, size_t smem = kKs2Smem) {
   if (a.n_items <= 0) return 0;
   int grid = a.n_items < 2 * c->sm_count ? a.n_items : 2 * c->sm_count;
   size_t e0 = 0;
   if (c->profile) e0 = prof_event(c);
-  kernel<<<grid, kThreads, kKs2Smem, c->stream>>>(a);
+  kernel<<<grid, kThreads, smem, c->stream>>>(a);
   if (c->profile) {
     size_t e1 = prof_event(c);
     c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
@@ -652,6 +654,7 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
   a.n_steps = n_dig;
   for (int s = 0; s < n_dig; s++) a.mat[s] = mats + (size_t)s * c->ggsw_prep_len();
   a.mat_div = mat_div; a.mat_stride = mat_stride;
+  if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ext2, a, KC_EXT, kExt2Smem);
   return launch(c, K_EXT, a, smem_bytes(3, 2, false), KC_EXT);
 }
 // chain of { glwe_rsh(1); automorphism_add with trace key i } for i in [g0, g1)
@@ -935,7 +938,9 @@ static int batch_chunk(const fheram_ram* r) {
   size_t budget = (size_t)3 << 30;  // bytes per arena
   int ch = (int)(budget / (per_read ? per_read : 1));
   if (ch < 1) ch = 1;
-  if (ch > 64) ch = 64;
+  int cap = 64;
+  if (const char* e = getenv("FHERAM_CHUNK")) { int v = atoi(e); if (v > 0) cap = v; }
+  if (ch > cap) ch = cap;
   return ch;
 }
 

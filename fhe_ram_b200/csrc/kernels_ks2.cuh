@@ -140,6 +140,224 @@ __device__ __forceinline__ void inv_transform2(double2 (&x)[8], double2* work, i
   radix8_inv<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
 }
 
+// ======================================================================================
+// k_ext2: external-product chains with TWO CTAs per SM.  Of the six input spectra four live in
+// tensor memory (128 columns per thread) and two in shared memory; pass-4 twiddles sit in a
+// 16 KiB shared table, pass-3 twiddles in __constant__ (8 distinct addresses per warp).
+// 32 (exchange) + 64 (two spectra) + 16 (twiddles) = 112 KiB shared memory, 256 TMEM columns,
+// <= 128 registers per CTA.  Same arithmetic and results as k_vmp<3,2,4,3,MODE_EXT>.
+// ======================================================================================
+__constant__ double2 c_tw3[256];  // zeta(6,B) | zeta(7,2B) | zeta(8,2k)   (Twiddles::tw6/tw7c/tw8c)
+
+struct Tw3 { double2 a, b, c, d; };
+__device__ __forceinline__ Tw3 load_tw3(int w, int lane) {
+  const int B = 8 * w + (lane >> 2);
+  Tw3 t;
+  t.a = c_tw3[B]; t.b = c_tw3[64 + B]; t.c = c_tw3[128 + 2 * B]; t.d = c_tw3[128 + 2 * B + 1];
+  return t;
+}
+
+constexpr size_t kExt2Smem = (size_t)kM * sizeof(double2) * 3 + (size_t)4 * kThreads * sizeof(double2) + 16;
+
+__global__ void __launch_bounds__(kThreads, 2) k_ext2(const VmpArgs A) {
+  constexpr int NR = 6, LOUT = 4, LRES = 3, NOUT = 2 * LOUT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* work = reinterpret_cast<double2*>(smem_raw);
+  double2* rows_s = work + kM;                 // spectra of rows 4 and 5
+  double2* tw4s = rows_s + 2 * kM;             // [4][256] pass-4 twiddles, thread-private columns
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tw4s + 4 * kThreads);
+
+  const int T = threadIdx.x, w = T >> 5, lane = T & 31;
+  constexpr double kInvM = 1.0 / (double)kM;
+  auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
+
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const int B4 = 32 * w + lane;
+    tw4s[0 * kThreads + T] = __ldg(A.tw.tw9 + 2 * B4);
+    tw4s[1 * kThreads + T] = __ldg(A.tw.tw9 + 2 * B4 + 1);
+    tw4s[2 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4);
+    tw4s[3 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4 + 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_s;
+  const uint32_t tsp = tmem_base + ((uint32_t)((w & 3) * 32) << 16) + 128 * (w >> 2);  // rows 0..3
+  const int P0 = 256 * w + lane;
+  long long phase_t0 = A.phase_cycles ? clock64() : 0;
+
+  for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    int* dst = A.dst + (size_t)item * A.ct_stride;
+    const int* src;
+    {
+      long idx = item;
+      if (A.src_div > 0) idx = item / A.src_div;
+      else if (A.src_mod > 0) { int r = item % A.src_mod; idx = A.src_map ? A.src_map[r] : r; }
+      src = A.src + idx * A.ct_stride;
+    }
+    const size_t mat_off = A.mat_div > 0 ? (size_t)(item / A.mat_div) * A.mat_stride : 0;
+
+    for (int step = 0; step < A.n_steps; step++) {
+      const double2* G = A.mat[step] + mat_off;
+      const int* xin = step > 0 ? dst : src;
+      PHASE_TICK(0);
+      // --------------------------- forward transforms ------------------------------
+      {
+        int nx[16];
+        auto load_row = [&](int rho, int (&v)[16]) {
+          const int* p = xin + CT(rho & 1, rho >> 1);
+#pragma unroll
+          for (int m = 0; m < 8; m++) { v[m] = p[T + 256 * m]; v[m + 8] = p[T + 256 * m + kM]; }
+        };
+        load_row(0, nx);
+#pragma unroll 1
+        for (int rho = 0; rho < NR; rho++) {
+          double2 x[8];
+#pragma unroll
+          for (int m = 0; m < 8; m++) x[m] = make_double2((double)nx[m], (double)nx[m + 8]);
+          if (rho + 1 < NR) load_row(rho + 1, nx);
+          fwd_pass1_store(x, work, T);
+          __syncthreads();
+          {
+            double2* base = work + 256 * w;
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = base[S1(lane + 32 * m)];
+            radix8_fwd<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
+#pragma unroll
+            for (int m = 0; m < 8; m++) base[S1(lane + 32 * m)] = x[m];
+            __syncwarp();
+            const int qr = 32 * (lane >> 2) + (lane & 3);
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = base[S1(qr + 4 * m)];
+            {
+              const Tw3 t = load_tw3(w, lane);
+              radix8_fwd<true>(x, t.a, t.b, t.c, t.d);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 8; m++) base[S2(qr + 4 * m)] = x[m];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = base[S2(8 * lane + j)];
+            {
+              const double2 b4a = tw4s[T], b4b = tw4s[kThreads + T], c4a = tw4s[2 * kThreads + T], c4b = tw4s[3 * kThreads + T];
+              bf(x[0], x[2], b4a); bf(x[1], x[3], b4a); bf(x[4], x[6], b4b); bf(x[5], x[7], b4b);
+              bf(x[0], x[1], c4a); bf(x[2], x[3], mul_i(c4a));
+              bf(x[4], x[5], c4b); bf(x[6], x[7], mul_i(c4b));
+            }
+          }
+          if (rho < 4) {
+            const double2 lo[4] = {x[0], x[1], x[2], x[3]};
+            const double2 hi[4] = {x[4], x[5], x[6], x[7]};
+            tm_st4(tsp + 32 * rho, lo);
+            tm_st4(tsp + 32 * rho + 16, hi);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) rows_s[(size_t)(rho - 4) * kM + P0 + 32 * j] = x[j];
+          }
+          __syncthreads();  // `work` is reused by the next row
+        }
+        tm_wait_st();
+      }
+      PHASE_TICK(2);
+
+      // --------------- contraction + inverse transform + epilogue ------------------
+#pragma unroll 1
+      for (int co = 0; co < 2; co++) {
+        int carry[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) carry[q] = 0;
+#pragma unroll 1
+        for (int l = LOUT - 1; l >= 0; l--) {
+          const int o = co * LOUT + l;
+          double2 cur[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) cur[j] = make_double2(0.0, 0.0);
+#pragma unroll 1
+          for (int rho = 0; rho < NR; rho++) {
+            const double2* gp = G + ((size_t)rho * NOUT + o) * kM + P0;
+            double2 g[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] = __ldg(gp + 32 * j);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              double2 a[4];
+              if (rho < 4) {
+                tm_ld4(tsp + 32 * rho + 16 * h, a);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[j] = rows_s[(size_t)(rho - 4) * kM + P0 + 32 * (4 * h + j)];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                cur[4 * h + j].x = fma(a[j].x, g[4 * h + j].x, fma(-a[j].y, g[4 * h + j].y, cur[4 * h + j].x));
+                cur[4 * h + j].y = fma(a[j].x, g[4 * h + j].y, fma(a[j].y, g[4 * h + j].x, cur[4 * h + j].y));
+              }
+            }
+          }
+          PHASE_TICK(3);
+          // inverse transform (pass-4 twiddles from shared, pass-3 from constant memory)
+          {
+            double2 (&x)[8] = cur;
+            double2* wb = work + 256 * w;
+            {
+              const double2 b4a = tw4s[T], b4b = tw4s[kThreads + T], c4a = tw4s[2 * kThreads + T], c4b = tw4s[3 * kThreads + T];
+              ibf(x[0], x[1], c4a); ibf(x[2], x[3], mul_i(c4a));
+              ibf(x[4], x[5], c4b); ibf(x[6], x[7], mul_i(c4b));
+              ibf(x[0], x[2], b4a); ibf(x[1], x[3], b4a); ibf(x[4], x[6], b4b); ibf(x[5], x[7], b4b);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) wb[S2(8 * lane + j)] = x[j];
+            __syncwarp();
+            const int qr = 32 * (lane >> 2) + (lane & 3);
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = wb[S2(qr + 4 * m)];
+            {
+              const Tw3 t = load_tw3(w, lane);
+              radix8_inv<true>(x, t.a, t.b, t.c, t.d);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 8; m++) wb[S1(qr + 4 * m)] = x[m];
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = wb[S1(lane + 32 * m)];
+            radix8_inv<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
+#pragma unroll
+            for (int m = 0; m < 8; m++) wb[S1(lane + 32 * m)] = x[m];
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 8; m++) x[m] = work[S1(T + 256 * m)];
+            __syncthreads();
+            radix8_inv<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
+          }
+          PHASE_TICK(4);
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const int i = T + 256 * (q & 7) + (q >> 3) * kM;
+            const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
+            const long long t = __double2ll_rn(v * kInvM) + (long long)carry[q];
+            const int c = (int)((t + 65536) >> kK);
+            const int dg = (int)t - (c << kK);
+            carry[q] = c;
+            if (l < LRES) dst[CT(co, l) + i] = dg;
+          }
+          PHASE_TICK(5);
+        }
+      }
+    }  // steps
+    __syncthreads();
+    PHASE_TICK(6);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+}
+
 constexpr size_t kKs2Smem = (size_t)kM * sizeof(double2) + (size_t)2 * kN * sizeof(long long) + 16;
 
 template <int MODE>
