@@ -309,7 +309,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
   const int T = threadIdx.x, w = T >> 5, lane = T & 31;
   const Tw34 tw = load_tw34(A.tw, w, lane);
   constexpr int NOUT = 2 * LOUT;
-  constexpr double kInvM = 1.0 / (double)kM;
   // layout of a ciphertext buffer: [limb][col][N]
   auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
 
@@ -488,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
           for (int q = 0; q < 16; q++) {
             const int i = T + 256 * (q & 7) + (q >> 3) * kM;
             const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
-            long long big = __double2ll_rn(v * kInvM);
+            long long big = __double2ll_rn(v);
             bool neg = false;
             if (MODE == MODE_TRACE) {
               // x +/- phi(KS(x)), KS(x) = vmp + body:  phi(body) gathered above
@@ -590,7 +589,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_prepare(const PrepArgs A) {
   __syncwarp();
   double2* out = A.out + (size_t)mat * A.out_stride + ((size_t)rho * 2 * A.lout + o) * kM;
 #pragma unroll
-  for (int j = 0; j < 8; j++) out[256 * w + 32 * j + lane] = spec[256 * w + 32 * j + lane];
+  for (int j = 0; j < 8; j++) {
+    // the 1/M of the inverse transform is folded into the prepared matrix (exact: power of two)
+    const double2 v = spec[256 * w + 32 * j + lane];
+    out[256 * w + 32 * j + lane] = make_double2(v.x * (1.0 / kM), v.y * (1.0 / kM));
+  }
 }
 
 // ======================================================================================

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext2(const VmpArgs A) {
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tw4s + 4 * kThreads);
 
   const int T = threadIdx.x, w = T >> 5, lane = T & 31;
-  constexpr double kInvM = 1.0 / (double)kM;
   auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
 
   if (w == 0) {
@@ -340,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext2(const VmpArgs A) {
           for (int q = 0; q < 16; q++) {
             const int i = T + 256 * (q & 7) + (q >> 3) * kM;
             const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
-            const long long t = __double2ll_rn(v * kInvM) + (long long)carry[q];
+            const long long t = __double2ll_rn(v) + (long long)carry[q];
             const int c = (int)((t + 65536) >> kK);
             const int dg = (int)t - (c << kK);
             carry[q] = c;
@@ -370,7 +369,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks2(const VmpArgs A) {
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(xp + 2 * kN);
 
   const int T = threadIdx.x, w = T >> 5, lane = T & 31;
-  constexpr double kInvM = 1.0 / (double)kM;
   auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
 
   if (w == 0) {
@@ -413,6 +411,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks2(const VmpArgs A) {
       const int ginv = A.gal_inv[step];
 
       // ------------------------------ prologue ------------------------------------
+      // (fusing the next step's rsh into the digit loop was measured: the extra 64-bit field
+      // inserts cost more than the prologue they save)
       if (MODE == MODE_TRACE) {
         int rk = A.rot_const;
         if (A.rot_mod > 0) rk += A.rot_mul * (item % A.rot_mod);
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks2(const VmpArgs A) {
           for (int q = 0; q < 16; q++) {
             const int i = T + 256 * (q & 7) + (q >> 3) * kM;
             const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
-            long long big = __double2ll_rn(v * kInvM);
+            long long big = __double2ll_rn(v);
             bool neg = false;
             long long wd = 0;
             if (MODE == MODE_TRACE) {
