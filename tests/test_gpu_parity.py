@@ -367,3 +367,17 @@ def test_external_product_microbench_shape(scenario):
     got = api.external_product_batch(s.params, cts, ggsw)
     for i in (0, 147, 148, 299):
         assert np.array_equal(got[i], s.orc.external_product(cts[i], ggsw)), i
+
+
+def test_noise_stays_within_budget_over_write_cycles(built):
+    """§8(f).3 noise instrumentation: ten rpw/write cycles at random addresses; an untouched word and
+    every freshly written word keep decrypting with noise below the example's bound 2^-(k_pt+1), and
+    the growth per cycle is sub-bit (README.md:36: tens of millions of accesses before refresh)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import noise_growth
+    rows = noise_growth.run(max_addr_log2=13, word_size=1, cycles=10, verbose=False)
+    assert all(r[1] < -9 for r in rows)
+    assert all(r[2] < -9 for r in rows[1:])
+    assert rows[-1][1] - rows[1][1] < 6.0       # after the first write the noise floor moves slowly
