@@ -731,6 +731,13 @@ struct fheram_ram {
   DevBuf result;             // [B][word_size] results
   DevBuf wbuf;               // uploaded write words
   DevBuf all;                // results of a chunked batched read
+  struct HostPipe {          // fheram_ram_read_batch_host: double-buffered upload pipeline
+    struct Set { long long* stage = nullptr; fheram_address a; cudaEvent_t copied = nullptr, freed = nullptr; };
+    Set sets[2];
+    long long* out_stage = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int cap = 0;
+  } pipe;
 };
 
 static int ram_create(fheram_ctx* c, int shard, int n_shards, fheram_ram** out) {
@@ -766,6 +773,14 @@ extern "C" int fheram_ram_destroy(fheram_ram* r) {
   cudaSetDevice(r->c->device);
   cudaFree(r->data); cudaFree(r->tree); cudaFree(r->feed_map);
   r->bufA.release(); r->bufB.release(); r->partial.release(); r->result.release(); r->wbuf.release(); r->all.release();
+  for (auto& s : r->pipe.sets) {
+    cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
+    s.a.raw = nullptr; s.a.prep = nullptr;
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.freed) cudaEventDestroy(s.freed);
+  }
+  cudaFree(r->pipe.out_stage);
+  if (r->pipe.copy_stream) cudaStreamDestroy(r->pipe.copy_stream);
   delete r;
   return 0;
 }
@@ -1001,38 +1016,38 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
   const long L = c->ct_stride();
   const size_t per_addr = (size_t)d.n_ggsw * c->ggsw_raw_len();  // limbs per address
   int chunk = batch_chunk(r);
-  if (chunk > 32) chunk = 32;
   if (chunk > n) chunk = n;
-  struct Set { long long* stage = nullptr; fheram_address a; cudaEvent_t copied, freed; };
-  Set sets[2];
-  cudaStream_t copy_stream;
-  CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-  long long* out_stage = nullptr;
+  // staging buffers, events and the copy stream are created once per RAM handle and reused
+  // (cudaMalloc / cudaFree of gigabytes per call cost more than the copies they serve)
+  typedef fheram_ram::HostPipe::Set Set;
+  fheram_ram::HostPipe& hp = r->pipe;
   int rc = 0;
   auto cleanup = [&]() {
-    cudaStreamSynchronize(copy_stream);
+    cudaStreamSynchronize(hp.copy_stream);
     cudaStreamSynchronize(c->stream);
-    for (auto& s : sets) {
-      cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
-      s.a.raw = nullptr; s.a.prep = nullptr;
-      if (s.copied) cudaEventDestroy(s.copied);
-      if (s.freed) cudaEventDestroy(s.freed);
-    }
-    cudaFree(out_stage);
-    cudaStreamDestroy(copy_stream);
   };
 #define TRYC(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define CUC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
-  for (auto& s : sets) {
-    s.a.c = c; s.a.count = chunk;
-    s.copied = nullptr; s.freed = nullptr;
-    CUC(cudaMalloc(&s.stage, sizeof(long long) * chunk * per_addr));
-    CUC(cudaMalloc(&s.a.raw, sizeof(int) * chunk * per_addr));
-    CUC(cudaMalloc(&s.a.prep, sizeof(double2) * (size_t)chunk * d.n_ggsw * c->ggsw_prep_len()));
-    CUC(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming));
+  if (!hp.copy_stream) CU(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
+  if (hp.cap < chunk) {
+    for (auto& s : hp.sets) {
+      cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
+      s.stage = nullptr; s.a.raw = nullptr; s.a.prep = nullptr;
+      s.a.c = c;
+      CU(cudaMalloc(&s.stage, sizeof(long long) * chunk * per_addr));
+      CU(cudaMalloc(&s.a.raw, sizeof(int) * chunk * per_addr));
+      CU(cudaMalloc(&s.a.prep, sizeof(double2) * (size_t)chunk * d.n_ggsw * c->ggsw_prep_len()));
+      if (!s.copied) CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+      if (!s.freed) CU(cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming));
+    }
+    cudaFree(hp.out_stage);
+    hp.out_stage = nullptr;
+    CU(cudaMalloc(&hp.out_stage, sizeof(long long) * (size_t)chunk * ws * L));
+    hp.cap = chunk;
   }
-  CUC(cudaMalloc(&out_stage, sizeof(long long) * (size_t)chunk * ws * L));
+  Set* sets = hp.sets;
+  long long* out_stage = hp.out_stage;
+  cudaStream_t copy_stream = hp.copy_stream;
   const int n_chunks = (n + chunk - 1) / chunk;
   auto issue_copy = [&](int ci) -> int {
     Set& s = sets[ci & 1];
