@@ -365,21 +365,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
         const int* a = src;
         const int* b = src + A.ct_stride;
         const int tt = A.rot_const;  // t
-#pragma unroll 4
-        for (int m = 0; m < 16; m++) {
-          const int i = T + 256 * m;
-          bool neg;
-          int j = rot_index(i, tt, neg);  // (a X^-t)[i] = +/- a[(i + t) mod 2N]
+        // loads are staged four positions at a time ahead of the stores: the scratch stores may
+        // alias the source for the compiler, which would otherwise serialise one L2 round trip
+        // per coefficient
+#pragma unroll 1
+        for (int mc = 0; mc < 16; mc += 4) {
+          int av[4][2][3], bv[4][2][3];
+          bool ng[4];
 #pragma unroll
-          for (int col = 0; col < 2; col++) {
-            int a0 = a[CT(col, 0) + j], a1 = a[CT(col, 1) + j], a2 = a[CT(col, 2) + j];
-            if (neg) { a0 = -a0; a1 = -a1; a2 = -a2; }
-            int b0 = b[CT(col, 0) + i], b1 = b[CT(col, 1) + i], b2 = b[CT(col, 2) + i];
-            int d0, d1, d2;
-            rsh1_3(a0 - b0, a1 - b1, a2 - b2, d0, d1, d2);
-            xb[CT(col, 0) + i] = d0; xb[CT(col, 1) + i] = d1; xb[CT(col, 2) + i] = d2;
-            rsh1_3(a0 + b0, a1 + b1, a2 + b2, d0, d1, d2);
-            scr1[CT(col, 0) + i] = d0; scr1[CT(col, 1) + i] = d1; scr1[CT(col, 2) + i] = d2;
+          for (int mm = 0; mm < 4; mm++) {
+            const int i = T + 256 * (mc + mm);
+            const int j = rot_index(i, tt, ng[mm]);  // (a X^-t)[i] = +/- a[(i + t) mod 2N]
+#pragma unroll
+            for (int col = 0; col < 2; col++)
+#pragma unroll
+              for (int l = 0; l < 3; l++) { av[mm][col][l] = a[CT(col, l) + j]; bv[mm][col][l] = b[CT(col, l) + i]; }
+          }
+#pragma unroll
+          for (int mm = 0; mm < 4; mm++) {
+            const int i = T + 256 * (mc + mm);
+#pragma unroll
+            for (int col = 0; col < 2; col++) {
+              int a0 = av[mm][col][0], a1 = av[mm][col][1], a2 = av[mm][col][2];
+              if (ng[mm]) { a0 = -a0; a1 = -a1; a2 = -a2; }
+              const int b0 = bv[mm][col][0], b1 = bv[mm][col][1], b2 = bv[mm][col][2];
+              int d0, d1, d2;
+              rsh1_3(a0 - b0, a1 - b1, a2 - b2, d0, d1, d2);
+              xb[CT(col, 0) + i] = d0; xb[CT(col, 1) + i] = d1; xb[CT(col, 2) + i] = d2;
+              rsh1_3(a0 + b0, a1 + b1, a2 + b2, d0, d1, d2);
+              scr1[CT(col, 0) + i] = d0; scr1[CT(col, 1) + i] = d1; scr1[CT(col, 2) + i] = d2;
+            }
           }
         }
       }
@@ -482,6 +497,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
             }
           });
           PHASE_TICK(4);
+          int sv[16];  // small global operands of this output, requested together (see prologue note)
+          if (MODE == MODE_COMBINE2 && l < LRES) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) sv[q] = scr1[CT(co, l) + T + 256 * (q & 7) + (q >> 3) * kM];
+          } else if (MODE == MODE_EXPAND && co == 1 && has_small) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) sv[q] = xin[CT(0, l) + T + 256 * (q & 7) + (q >> 3) * kM];
+          } else if (MODE == MODE_AUTO && co == 0 && has_small) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+              bool ng;
+              sv[q] = xin[CT(0, l) + auto_index(T + 256 * (q & 7) + (q >> 3) * kM, ginv, ng)];
+            }
+          }
           // cur[m] = M * phi_g(vmp)[T + 256 m] (natural order; plain vmp for EXT / EXPAND)
 #pragma unroll
           for (int q = 0; q < 16; q++) {
@@ -495,12 +524,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
               if (A.sign < 0) big = -big;
               if (has_small) big += (long long)xb[CT(co, l) + i];
             } else if (MODE == MODE_EXPAND) {
-              if (co == 1 && has_small) big += (long long)xin[CT(0, l) + i];
+              if (co == 1 && has_small) big += (long long)sv[q];
             } else if (MODE == MODE_AUTO || MODE == MODE_COMBINE2) {
               // phi(normalize(KS(x))): run the carry chain in the pre-automorphism sign frame
               const int u = auto_index(i, ginv, neg);
               if (neg) big = -big;
-              if (co == 0 && has_small) big += (long long)xin[CT(0, l) + u];
+              if (co == 0 && has_small) big += (long long)(MODE == MODE_AUTO ? sv[q] : xin[CT(0, l) + u]);
             }
             const long long t = big + (long long)carryA[q];
             const int c = (int)((t + 65536) >> kK);
@@ -516,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
               } else if (MODE == MODE_COMBINE2) {
                 // y = phi(normalize(KS(D))); a' = normalize(S - y); out = a' X^t
                 const int y = neg ? -dg : dg;
-                const int t2 = scr1[CT(co, l) + i] - y + carry2A[q];
+                const int t2 = sv[q] - y + carry2A[q];
                 const int dg2 = sext17i(t2);
                 carry2A[q] = (t2 - dg2) >> kK;
                 bool rneg;

@@ -441,21 +441,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks2(const VmpArgs A) {
         const int* a = src;
         const int* b = src + A.ct_stride;
         const int tt = A.rot_const;
-#pragma unroll 4
-        for (int m = 0; m < 16; m++) {
-          const int i = T + 256 * m;
-          bool neg;
-          const int j = rot_index(i, tt, neg);
+        // loads staged four positions at a time ahead of the stores (see k_vmp)
+#pragma unroll 1
+        for (int mc = 0; mc < 16; mc += 4) {
+          int av[4][2][3], bv[4][2][3];
+          bool ng[4];
 #pragma unroll
-          for (int col = 0; col < 2; col++) {
-            int a0 = a[CT(col, 0) + j], a1 = a[CT(col, 1) + j], a2 = a[CT(col, 2) + j];
-            if (neg) { a0 = -a0; a1 = -a1; a2 = -a2; }
-            const int b0 = b[CT(col, 0) + i], b1 = b[CT(col, 1) + i], b2 = b[CT(col, 2) + i];
-            int d0, d1, d2;
-            rsh1_3(a0 - b0, a1 - b1, a2 - b2, d0, d1, d2);
-            xp[col * kN + i] = pack3(d0, d1, d2);
-            rsh1_3(a0 + b0, a1 + b1, a2 + b2, d0, d1, d2);
-            scr1[CT(col, 0) + i] = d0; scr1[CT(col, 1) + i] = d1; scr1[CT(col, 2) + i] = d2;
+          for (int mm = 0; mm < 4; mm++) {
+            const int i = T + 256 * (mc + mm);
+            const int j = rot_index(i, tt, ng[mm]);
+#pragma unroll
+            for (int col = 0; col < 2; col++)
+#pragma unroll
+              for (int l = 0; l < 3; l++) { av[mm][col][l] = a[CT(col, l) + j]; bv[mm][col][l] = b[CT(col, l) + i]; }
+          }
+#pragma unroll
+          for (int mm = 0; mm < 4; mm++) {
+            const int i = T + 256 * (mc + mm);
+#pragma unroll
+            for (int col = 0; col < 2; col++) {
+              int a0 = av[mm][col][0], a1 = av[mm][col][1], a2 = av[mm][col][2];
+              if (ng[mm]) { a0 = -a0; a1 = -a1; a2 = -a2; }
+              const int b0 = bv[mm][col][0], b1 = bv[mm][col][1], b2 = bv[mm][col][2];
+              int d0, d1, d2;
+              rsh1_3(a0 - b0, a1 - b1, a2 - b2, d0, d1, d2);
+              xp[col * kN + i] = pack3(d0, d1, d2);
+              rsh1_3(a0 + b0, a1 + b1, a2 + b2, d0, d1, d2);
+              scr1[CT(col, 0) + i] = d0; scr1[CT(col, 1) + i] = d1; scr1[CT(col, 2) + i] = d2;
+            }
           }
         }
       }
@@ -545,6 +558,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks2(const VmpArgs A) {
             }
           });
           PHASE_TICK(4);
+          int sv[16];  // COMBINE2: S digits of this output, requested together
+          if (MODE == MODE_COMBINE2 && l < LRES) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) sv[q] = scr1[CT(co, l) + T + 256 * (q & 7) + (q >> 3) * kM];
+          }
 #pragma unroll
           for (int q = 0; q < 16; q++) {
             const int i = T + 256 * (q & 7) + (q >> 3) * kM;
@@ -573,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks2(const VmpArgs A) {
                 xp[co * kN + i] = repack3(wd, l, dg);
               } else {
                 const int y = neg ? -dg : dg;
-                const int t2 = scr1[CT(co, l) + i] - y + carry2[q];
+                const int t2 = sv[q] - y + carry2[q];
                 const int dg2 = sext17i(t2);
                 carry2[q] = (t2 - dg2) >> kK;
                 bool rneg;
