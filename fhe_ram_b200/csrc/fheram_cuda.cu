@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "../../include/fheram.h"
 #include "kernels.cuh"
 #include "kernels_ks2.cuh"
+#include "kernels_ks3.cuh"
 
 using namespace fheram;
 
@@ -165,6 +167,7 @@ struct fheram_ctx {
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
   DevBuf opbuf[3];  // op-level entry points
+  DevBuf split_tmp[2];  // ping-pong ciphertexts of the column-split (latency) schedules
   long long* d_phase = nullptr;  // per-CTA phase cycle counters (fheram_debug_phase_cycles)
   // per-kernel-class CUDA-event timing (fheram_ctx_profile)
   bool profile = false;
@@ -191,6 +194,10 @@ static size_t smem_bytes(int R, int CIN, bool xsmem) {
 #define K_AUTO3    k_vmp<3, 1, 4, 3, MODE_AUTO, false>
 #define K_AUTO_INV k_vmp<4, 1, 5, 4, MODE_AUTO, false>
 #define K_EXPAND   k_vmp<4, 1, 5, 4, MODE_EXPAND, false>
+// column-split variants (two CTAs per operation, narrow launches)
+#define K_EXT_S      k_vmp<3, 2, 4, 3, MODE_EXT, false, true>
+#define K_TRACE_S    k_vmp<3, 1, 4, 3, MODE_TRACE, true, true>
+#define K_COMBINE2_S k_vmp<3, 1, 4, 3, MODE_COMBINE2, true, true>
 
 static int set_attrs() {
   CU(cudaFuncSetAttribute(K_EXT, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 2, false)));
@@ -199,8 +206,13 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(K_AUTO3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, false)));
   CU(cudaFuncSetAttribute(K_AUTO_INV, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
   CU(cudaFuncSetAttribute(K_EXPAND, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4, 1, false)));
+  CU(cudaFuncSetAttribute(K_EXT_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 2, false)));
+  CU(cudaFuncSetAttribute(K_TRACE_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
+  CU(cudaFuncSetAttribute(K_COMBINE2_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
   CU(cudaFuncSetAttribute(k_ext2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt2Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
+  CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
+  CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   return 0;
 }
@@ -282,7 +294,7 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->stage64.release(); c->scratch.release();
+  c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
   cudaFree(c->d_tw); cudaFree(c->d_err);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -482,11 +494,38 @@ static int launch(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem, int cl
   return 0;
 }
 
+// column-split launch (latency mode): two CTAs per item, single step
+static bool use_split(const fheram_ctx* c, int n_items) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_SPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && 2 * n_items <= c->sm_count;
+}
+template <typename K>
+static int launch_split(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem, int cls) {
+  if (a.n_items <= 0) return 0;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
+  kernel<<<2 * a.n_items, kThreads, smem, c->stream>>>(a);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
 // key-switch kernels built for two CTAs per SM (kernels_ks2.cuh); FHERAM_KS2=0 selects k_vmp
 static bool use_ks2() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FHERAM_KS2"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
+}
+// word-domain key-switch kernels (kernels_ks3.cuh); FHERAM_KS3=0 falls back to k_ks2 / k_vmp,
+// FHERAM_KS3=2 uses them for narrow launches as well
+static int ks3_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KS3"); v = e ? atoi(e) : 1; }
+  return v;
 }
 template <typename K>
 static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls, size_t smem = kKs2Smem) {
@@ -654,6 +693,23 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
   a.n_steps = n_dig;
   for (int s = 0; s < n_dig; s++) a.mat[s] = mats + (size_t)s * c->ggsw_prep_len();
   a.mat_div = mat_div; a.mat_stride = mat_stride;
+  if (use_split(c, n_items)) {
+    // narrow launch: one step per launch, two CTAs per ciphertext (one output column each),
+    // ping-pong between two temporaries because both CTAs read both input columns
+    const size_t bytes = sizeof(int) * (size_t)n_items * c->ct_stride();
+    TRY(c->split_tmp[0].ensure(bytes));
+    TRY(c->split_tmp[1].ensure(bytes));
+    for (int s = 0; s < n_dig; s++) {
+      VmpArgs b = a;
+      b.n_steps = 1;
+      b.mat[0] = a.mat[s];
+      if (s > 0) { b.src = (const int*)c->split_tmp[(s - 1) & 1].p; b.src_map = nullptr; b.src_mod = 0; b.src_div = 0; }
+      b.dst = (int*)c->split_tmp[s & 1].p;
+      TRY(launch_split(c, K_EXT_S, b, smem_bytes(3, 2, false), KC_EXT));
+    }
+    CU(cudaMemcpyAsync(dst, c->split_tmp[(n_dig - 1) & 1].p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+  }
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ext2, a, KC_EXT, kExt2Smem);
   return launch(c, K_EXT, a, smem_bytes(3, 2, false), KC_EXT);
 }
@@ -679,8 +735,28 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE);
+  if (use_split(c, n_items)) {
+    const size_t bytes = sizeof(int) * (size_t)n_items * c->ct_stride();
+    TRY(c->split_tmp[0].ensure(bytes));
+    TRY(c->split_tmp[1].ensure(bytes));
+    for (int s = 0; s < a.n_steps; s++) {
+      VmpArgs b = a;
+      b.n_steps = 1;
+      b.mat[0] = a.mat[s]; b.gal[0] = a.gal[s]; b.gal_inv[0] = a.gal_inv[s];
+      if (s > 0) {
+        b.src = (const int*)c->split_tmp[(s - 1) & 1].p;
+        b.src_map = nullptr; b.src_mod = 0; b.src_div = 0; b.rot_mod = 0; b.rot_mul = 0; b.rot_const = 0;
+      }
+      b.dst = (int*)c->split_tmp[s & 1].p;
+      TRY(launch_split(c, K_TRACE_S, b, smem_bytes(3, 1, true), KC_TRACE));
+    }
+    CU(cudaMemcpyAsync(dst, c->split_tmp[(a.n_steps - 1) & 1].p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+  }
   // wide launches: two lean CTAs per SM overlap each other's phases; narrow ones (at most one
   // item per SM) finish sooner with the single-CTA kernel
+  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_TRACE>, a, KC_TRACE);
   return launch(c, K_TRACE, a, smem_bytes(3, 1, true), KC_TRACE);
 }
@@ -693,6 +769,9 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2);
+  if (use_split(c, n_items)) return launch_split(c, K_COMBINE2_S, a, smem_bytes(3, 1, true), KC_COMBINE2);
+  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_COMBINE2>, a, KC_COMBINE2);
   return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }

@@ -299,7 +299,9 @@ struct VmpArgs {
 //   LOUT  limbs of the matrix / big result;   LRES  limbs kept after normalisation
 // Shared memory: R*CIN spectra (32 KiB each) + 32 KiB work + (XSMEM ? 2*R*N ints : 0).
 // ======================================================================================
-template <int R, int CIN, int LOUT, int LRES, int MODE, bool XSMEM>
+// SPLIT (latency mode for narrow launches): two CTAs share one operation, CTA (2*item + c) produces
+// output column c only (both transform the inputs redundantly); single-step launches, src != dst.
+template <int R, int CIN, int LOUT, int LRES, int MODE, bool XSMEM, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* spectra = reinterpret_cast<double2*>(smem_raw);
@@ -313,7 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
   auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
 
   long long phase_t0 = A.phase_cycles ? clock64() : 0;
-  for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+  const int my_co = SPLIT ? (blockIdx.x & 1) : 0;
+  for (int item = SPLIT ? (blockIdx.x >> 1) : blockIdx.x; item < A.n_items; item += SPLIT ? (gridDim.x >> 1) : gridDim.x) {
     int* dst = A.dst + (size_t)item * A.ct_stride;
     int* scr0 = A.scratch ? A.scratch + (size_t)blockIdx.x * 2 * A.ct_stride : nullptr;
     int* scr1 = scr0 ? scr0 + A.ct_stride : nullptr;
@@ -467,6 +470,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
           const double2* gp = G + ((size_t)rho * NOUT + l) * kM + P0;
           const double2* ap = spectra + (size_t)rho * kM + P0;
           double2 g0[8], g1[8];
+          if (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) g0[j] = __ldg(gp + (size_t)my_co * LOUT * kM + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const double2 a = ap[32 * j];
+              cur[j].x = fma(a.x, g0[j].x, fma(-a.y, g0[j].y, cur[j].x));
+              cur[j].y = fma(a.x, g0[j].y, fma(a.y, g0[j].x, cur[j].y));
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 8; j++) { g0[j] = __ldg(gp + 32 * j); g1[j] = __ldg(gp + (size_t)LOUT * kM + 32 * j); }
 #pragma unroll
@@ -480,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
         }
         PHASE_TICK(3);
 #pragma unroll 1
-        for (int co = 0; co < 2; co++) {
+        for (int co = SPLIT ? my_co : 0; co < (SPLIT ? my_co + 1 : 2); co++) {
           const bool has_small = l < R;  // the small operand has R limbs
           int xnat[16];  // MODE_TRACE: phi_g(x) body limb; read before any thread overwrites the
                          // buffer in place, i.e. between the two barriers of the inverse transform
@@ -556,12 +570,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
           }
           PHASE_TICK(5);
           // rotate the per-column state so the loop body always works on (cur, carryA, carry2A)
+          // (split mode handles one column only: nothing to rotate)
+          if (!SPLIT) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) { const double2 t = cur[j]; cur[j] = nxt[j]; nxt[j] = t; }
+            for (int j = 0; j < 8; j++) { const double2 t = cur[j]; cur[j] = nxt[j]; nxt[j] = t; }
 #pragma unroll
-          for (int q = 0; q < 16; q++) {
-            int t = carryA[q]; carryA[q] = carryB[q]; carryB[q] = t;
-            if (MODE == MODE_COMBINE2) { t = carry2A[q]; carry2A[q] = carry2B[q]; carry2B[q] = t; }
+            for (int q = 0; q < 16; q++) {
+              int t = carryA[q]; carryA[q] = carryB[q]; carryB[q] = t;
+              if (MODE == MODE_COMBINE2) { t = carry2A[q]; carry2A[q] = carry2B[q]; carry2B[q] = t; }
+            }
           }
         }
       }
@@ -569,8 +586,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
     }  // steps
 
     if (MODE == MODE_TRACE) {
-      // copy the in-place result to dst (coalesced)
-      for (int i = T; i < 2 * R * kN; i += kThreads) dst[i] = xb[i];
+      // copy the in-place result to dst (coalesced); split mode: this CTA's column only
+      for (int i = T; i < 2 * R * kN; i += kThreads)
+        if (!SPLIT || ((i / kN) & 1) == my_co) dst[i] = xb[i];
     }
     __syncthreads();  // xb / spectra reuse by the next item
     PHASE_TICK(6);
