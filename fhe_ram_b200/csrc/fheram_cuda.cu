@@ -210,9 +210,10 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(K_TRACE_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
   CU(cudaFuncSetAttribute(K_COMBINE2_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
   CU(cudaFuncSetAttribute(k_ext2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt2Smem));
+  CU(cudaFuncSetAttribute(k_ext3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt3Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
-  CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
-  CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
+  CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
+  CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   return 0;
 }
@@ -273,6 +274,9 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   for (int b = 0; b < 64; b++) zeta(7, 2 * b, q++);
   for (int b = 0; b < 128; b++) zeta(8, 2 * b, q++);
   for (int b = 0; b < 512; b++) zeta(9, b, q++);
+  // zeta(9, 2k+1) = i zeta(9, 2k): make the table satisfy it bit for bit, so kernels that derive the
+  // odd entry (k_ext3) agree exactly with those that load it
+  for (int b = 1; b < 512; b += 2) q[b - 512] = make_double2(-q[b - 513].y, q[b - 513].x);
   for (int b = 0; b < 512; b++) zeta(10, 2 * b, q++);
   CU(cudaMemcpyToSymbol(c_tw_lo, lo.data(), sizeof(double2) * 64));
   CU(cudaMemcpyToSymbol(c_tw3, hi.data(), sizeof(double2) * 256));  // tw6 | tw7c | tw8c
@@ -710,6 +714,7 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
     CU(cudaMemcpyAsync(dst, c->split_tmp[(n_dig - 1) & 1].p, bytes, cudaMemcpyDeviceToDevice, c->stream));
     return 0;
   }
+  if (ks3_mode() >= 1 && n_items > c->sm_count) return launch_ks2(c, k_ext3, a, KC_EXT, kExt3Smem);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ext2, a, KC_EXT, kExt2Smem);
   return launch(c, K_EXT, a, smem_bytes(3, 2, false), KC_EXT);
 }
@@ -735,7 +740,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
-  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE);
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
   if (use_split(c, n_items)) {
     const size_t bytes = sizeof(int) * (size_t)n_items * c->ct_stride();
     TRY(c->split_tmp[0].ensure(bytes));
@@ -756,7 +761,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   }
   // wide launches: two lean CTAs per SM overlap each other's phases; narrow ones (at most one
   // item per SM) finish sooner with the single-CTA kernel
-  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE);
+  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_TRACE>, a, KC_TRACE);
   return launch(c, K_TRACE, a, smem_bytes(3, 1, true), KC_TRACE);
 }
@@ -769,9 +774,9 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
-  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2);
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
   if (use_split(c, n_items)) return launch_split(c, K_COMBINE2_S, a, smem_bytes(3, 1, true), KC_COMBINE2);
-  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2);
+  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_COMBINE2>, a, KC_COMBINE2);
   return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }

@@ -21,6 +21,7 @@
 // 616-629 (Poulpy 0.3.2 glwe_trace, glwe_packer; oracle/fheram_oracle.c glwe_trace, pack_combine).
 #pragma once
 #include "kernels_ks2.cuh"
+#include "transform_pad.cuh"
 
 namespace fheram {
 
@@ -54,13 +55,172 @@ __device__ __forceinline__ unsigned long long magic_bits(double t) {
   return ((unsigned long long)(uint32_t)__double2hiint(t) << 32) | (uint32_t)__double2loint(t);
 }
 
+// ======================================================================================
+// k_ext3: k_ext2 with the padded exchange buffer of transform_pad.cuh (addresses are base + immediate
+// instead of XOR swizzles), three instead of four pass-4 twiddle columns, and digits converted with
+// one DADD instead of I2F.  Same arithmetic and results.
+// ======================================================================================
+// int32 -> double as (2^52 + 2^31 + v) - (2^52 + 2^31)
+__device__ __forceinline__ double int_f64(int v) {
+  return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// 36 (padded exchange buffer) + 64 (two spectra) + 12 (pass-4 twiddles b4a, c4a, c4b; b4b = i b4a) = 112 KiB
+constexpr size_t kExt3Smem = (size_t)kWorkPad * sizeof(double2) + (size_t)2 * kM * sizeof(double2) +
+                             (size_t)3 * kThreads * sizeof(double2) + 16;
+
+__global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
+  constexpr int NR = 6, LOUT = 4, LRES = 3, NOUT = 2 * LOUT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* work = reinterpret_cast<double2*>(smem_raw);
+  double2* rows_s = work + kWorkPad;           // spectra of rows 4 and 5
+  double2* tw4s = rows_s + 2 * kM;             // [3][256] pass-4 twiddles, thread-private columns
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tw4s + 3 * kThreads);
+
+  const int T = threadIdx.x, w = T >> 5, lane = T & 31;
+  auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
+
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const int B4 = 32 * w + lane;
+    tw4s[0 * kThreads + T] = __ldg(A.tw.tw9 + 2 * B4);  // zeta(9, 2 B4 + 1) = i * this one
+    tw4s[1 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4);
+    tw4s[2 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4 + 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_s;
+  const uint32_t tsp = tmem_base + ((uint32_t)((w & 3) * 32) << 16) + 128 * (w >> 2);  // rows 0..3
+  const int P0 = 256 * w + lane;
+  const PadAddr pa = pad_addr(work, T, w, lane);
+  auto tw3 = [&]() { const Tw3 t = load_tw3(w, lane); return Tw4x{t.a, t.b, t.c, t.d}; };
+  auto tw4 = [&]() {
+    const double2 b4a = tw4s[T];
+    return Tw4x{b4a, mul_i(b4a), tw4s[kThreads + T], tw4s[2 * kThreads + T]};
+  };
+  long long phase_t0 = A.phase_cycles ? clock64() : 0;
+
+  for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    int* dst = A.dst + (size_t)item * A.ct_stride;
+    const int* src;
+    {
+      long idx = item;
+      if (A.src_div > 0) idx = item / A.src_div;
+      else if (A.src_mod > 0) { int r = item % A.src_mod; idx = A.src_map ? A.src_map[r] : r; }
+      src = A.src + idx * A.ct_stride;
+    }
+    const size_t mat_off = A.mat_div > 0 ? (size_t)(item / A.mat_div) * A.mat_stride : 0;
+
+    for (int step = 0; step < A.n_steps; step++) {
+      const double2* G = A.mat[step] + mat_off;
+      const int* xin = step > 0 ? dst : src;
+      PHASE_TICK(0);
+      // --------------------------- forward transforms ------------------------------
+      {
+        int nx[16];
+        auto load_row = [&](int rho, int (&v)[16]) {
+          const int* p = xin + CT(rho & 1, rho >> 1);
+#pragma unroll
+          for (int m = 0; m < 8; m++) { v[m] = p[T + 256 * m]; v[m + 8] = p[T + 256 * m + kM]; }
+        };
+        load_row(0, nx);
+#pragma unroll 1
+        for (int rho = 0; rho < NR; rho++) {
+          double2 x[8];
+#pragma unroll
+          for (int m = 0; m < 8; m++) x[m] = make_double2(int_f64(nx[m]), int_f64(nx[m + 8]));
+          if (rho + 1 < NR) load_row(rho + 1, nx);
+          fwd_pass1_store_p(x, pa);
+          __syncthreads();
+          fwd_warp_passes_p(pa, w, tw3, tw4, x);
+          if (rho < 4) {
+            const double2 lo[4] = {x[0], x[1], x[2], x[3]};
+            const double2 hi[4] = {x[4], x[5], x[6], x[7]};
+            tm_st4(tsp + 32 * rho, lo);
+            tm_st4(tsp + 32 * rho + 16, hi);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) rows_s[(size_t)(rho - 4) * kM + P0 + 32 * j] = x[j];
+          }
+          __syncthreads();  // `work` is reused by the next row
+        }
+        tm_wait_st();
+      }
+      PHASE_TICK(2);
+
+      // --------------- contraction + inverse transform + epilogue ------------------
+#pragma unroll 1
+      for (int co = 0; co < 2; co++) {
+        int carry[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) carry[q] = 0;
+#pragma unroll 1
+        for (int l = LOUT - 1; l >= 0; l--) {
+          const int o = co * LOUT + l;
+          double2 cur[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) cur[j] = make_double2(0.0, 0.0);
+#pragma unroll 1
+          for (int rho = 0; rho < NR; rho++) {
+            const double2* gp = G + ((size_t)rho * NOUT + o) * kM + P0;
+            double2 g[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] = __ldg(gp + 32 * j);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              double2 a[4];
+              if (rho < 4) {
+                tm_ld4(tsp + 32 * rho + 16 * h, a);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[j] = rows_s[(size_t)(rho - 4) * kM + P0 + 32 * (4 * h + j)];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                cur[4 * h + j].x = fma(a[j].x, g[4 * h + j].x, fma(-a[j].y, g[4 * h + j].y, cur[4 * h + j].x));
+                cur[4 * h + j].y = fma(a[j].x, g[4 * h + j].y, fma(a[j].y, g[4 * h + j].x, cur[4 * h + j].y));
+              }
+            }
+          }
+          PHASE_TICK(3);
+          inv_transform_p(cur, pa, w, tw3, tw4);
+          PHASE_TICK(4);
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            const int i = T + 256 * (q & 7) + (q >> 3) * kM;
+            const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
+            const long long t = __double2ll_rn(v) + (long long)carry[q];
+            const int c = (int)((t + 65536) >> kK);
+            const int dg = (int)t - (c << kK);
+            carry[q] = c;
+            if (l < LRES) dst[CT(co, l) + i] = dg;
+          }
+          PHASE_TICK(5);
+        }
+      }
+    }  // steps
+    __syncthreads();
+    PHASE_TICK(6);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+}
+
+
+constexpr size_t kKs3Smem = (size_t)kWorkPad * sizeof(double2) + (size_t)2 * kN * sizeof(long long) + 16;
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
   static_assert(MODE == MODE_TRACE || MODE == MODE_COMBINE2, "key-switch modes only");
   constexpr int R = 3, LOUT = 4, NOUT = 2 * LOUT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* work = reinterpret_cast<double2*>(smem_raw);
-  unsigned long long* xp = reinterpret_cast<unsigned long long*>(work + kM);  // [2 cols][N] words
+  double2* work = reinterpret_cast<double2*>(smem_raw);  // padded exchange buffer (transform_pad.cuh)
+  unsigned long long* xp = reinterpret_cast<unsigned long long*>(work + kWorkPad);  // [2 cols][N] words
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(xp + 2 * kN);
 
   const int T = threadIdx.x, w = T >> 5, lane = T & 31;
@@ -86,6 +246,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
     tm_wait_st();
   }
   const int P0 = 256 * w + lane;
+  const PadAddr pa = pad_addr(work, T, w, lane);
+  auto tw3 = [&]() { double2 t[4]; tm_ld4(ttw, t); return Tw4x{t[0], t[1], t[2], t[3]}; };
+  auto tw4 = [&]() { double2 t[4]; tm_ld4(ttw + 16, t); return Tw4x{t[0], t[1], t[2], t[3]}; };
   const double sgn_d = (MODE == MODE_TRACE && A.sign < 0) ? -1.0 : 1.0;
   const uint32_t sgn_bit = (MODE == MODE_TRACE && A.sign < 0) ? 1u : 0u;
   long long phase_t0 = A.phase_cycles ? clock64() : 0;
@@ -171,18 +334,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
 
       // --------------------------- forward transforms ------------------------------
       {
-        // phi_g(x) mask words of the 16 input positions, gathered once for all limbs; bit 31 of
-        // the high half carries the automorphism sign of the position
-        uint32_t mlo[16], mhi[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-          const int e = (e0 + (q & 7) * d1 + (q >> 3) * d2) & (2 * kN - 1);
-          const unsigned long long wd = xp[kN + (e & (kN - 1))];
-          const uint32_t ng = e >= kN ? 1u : 0u;
-          mlo[q] = (uint32_t)wd;
-          mhi[q] = (uint32_t)(wd >> 32) | (ng << 31);
-          sgn |= ng << q;
-        }
+        // phi_g(x) mask digits of the 16 input positions; the words are gathered again for every
+        // limb (holding them across the three transforms costs 32 registers and spills)
 #pragma unroll 1
         for (int rho = 0; rho < R; rho++) {
           double2 x[8];
@@ -191,13 +344,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
           // 48 digits out of the loop and spills them)
           const int s1 = rho == 0 ? 31 : (rho == 1 ? 17 : 0);
           const int s2 = rho == 0 ? 3 : 0;
+          unsigned sg = 0;
 #pragma unroll
-          for (int m = 0; m < 8; m++)
-            x[m] = make_double2(field_f64((__funnelshift_r(mlo[m], mhi[m], s1) >> s2) & 0x1ffffu, mhi[m] & 0x80000000u),
-                                field_f64((__funnelshift_r(mlo[m + 8], mhi[m + 8], s1) >> s2) & 0x1ffffu, mhi[m + 8] & 0x80000000u));
-          fwd_pass1_store(x, work, T);
+          for (int m = 0; m < 8; m++) {
+            const int ea = (e0 + m * d1) & (2 * kN - 1);
+            const int eb = (ea + d2) & (2 * kN - 1);
+            const unsigned long long wa = xp[kN + (ea & (kN - 1))];
+            const unsigned long long wb = xp[kN + (eb & (kN - 1))];
+            const uint32_t na = ea >= kN ? 0x80000000u : 0u, nb = eb >= kN ? 0x80000000u : 0u;
+            sg |= (na >> (31 - m)) | (nb >> (23 - m));
+            x[m] = make_double2(
+                field_f64((__funnelshift_r((uint32_t)wa, (uint32_t)(wa >> 32), s1) >> s2) & 0x1ffffu, na),
+                field_f64((__funnelshift_r((uint32_t)wb, (uint32_t)(wb >> 32), s1) >> s2) & 0x1ffffu, nb));
+          }
+          sgn = sg;
+          fwd_pass1_store_p(x, pa);
           __syncthreads();
-          fwd_warp_passes2(work, w, lane, ttw, x);
+          fwd_warp_passes_p(pa, w, tw3, tw4, x);
           {
             const double2 lo[4] = {x[0], x[1], x[2], x[3]};
             const double2 hi[4] = {x[4], x[5], x[6], x[7]};
@@ -241,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
             }
           }
           PHASE_TICK(3);
-          inv_transform2(cur, work, T, w, lane, ttw, []() {});
+          inv_transform_p(cur, pa, w, tw3, tw4);
           PHASE_TICK(4);
           // cur[m] = phi_g(vmp)[T + 256 m] (+ i * [.. + 2048]); round and accumulate into the word
           if (l == 3) {
