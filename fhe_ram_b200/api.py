@@ -18,12 +18,13 @@ or GPU raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "libfheram_cuda.so"
+_LIB_PATH = Path(os.environ.get("FHERAM_LIB", _PKG / "libfheram_cuda.so"))  # FHERAM_LIB: dev builds (tools/ablate.sh)
 
 
 class FheRamError(RuntimeError):

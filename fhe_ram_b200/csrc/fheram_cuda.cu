@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "kernels_ks2.cuh"
 #include "kernels_ks3.cuh"
+#include "kernels_ks4.cuh"
 
 using namespace fheram;
 
@@ -214,6 +215,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
+  CU(cudaFuncSetAttribute(k_ks4<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
+  CU(cudaFuncSetAttribute(k_ks4<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   return 0;
 }
@@ -531,6 +534,12 @@ static int ks3_mode() {
   if (v < 0) { const char* e = getenv("FHERAM_KS3"); v = e ? atoi(e) : 1; }
   return v;
 }
+// FHERAM_KSGEN=3 selects k_ks3 instead of the pipelined k_ks4 (kernels_ks4.cuh) where ks3_mode() applies
+static bool use_ks4() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KSGEN"); v = (e && atoi(e) == 3) ? 0 : 1; }
+  return v == 1;
+}
 template <typename K>
 static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls, size_t smem = kKs2Smem) {
   if (a.n_items <= 0) return 0;
@@ -740,6 +749,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
+  if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
   if (use_split(c, n_items)) {
     const size_t bytes = sizeof(int) * (size_t)n_items * c->ct_stride();
@@ -761,7 +771,8 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   }
   // wide launches: two lean CTAs per SM overlap each other's phases; narrow ones (at most one
   // item per SM) finish sooner with the single-CTA kernel
-  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
+  if (ks3_mode() == 1 && n_items > c->sm_count && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
+  if (ks3_mode() == 1 && n_items > c->sm_count) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_TRACE>, a, KC_TRACE);
   return launch(c, K_TRACE, a, smem_bytes(3, 1, true), KC_TRACE);
 }
@@ -774,9 +785,11 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
   if (use_split(c, n_items)) return launch_split(c, K_COMBINE2_S, a, smem_bytes(3, 1, true), KC_COMBINE2);
-  if (ks3_mode() >= 2 || (ks3_mode() == 1 && n_items > c->sm_count)) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
+  if (ks3_mode() == 1 && n_items > c->sm_count && use_ks4()) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
+  if (ks3_mode() == 1 && n_items > c->sm_count) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
   if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_COMBINE2>, a, KC_COMBINE2);
   return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }

@@ -23,6 +23,12 @@
 #include "kernels_ks2.cuh"
 #include "transform_pad.cuh"
 
+// timing ablations for tools/ablate.sh (results are garbage when non-zero): 1 no matrix loads,
+// 2 no inverse transforms, 4 no forward transforms
+#ifndef FHERAM_ABL
+#define FHERAM_ABL 0
+#endif
+
 namespace fheram {
 
 constexpr unsigned long long kBias51 = (1ull << 16) | (1ull << 33) | (1ull << 50);
@@ -84,6 +90,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  BufSync bs{smem_u32(tmem_base_s + 2), 0u};  // exchange-buffer mbarrier in the same 16-byte slot
+  if (T == 0) buf_init(bs.mbar);
   {
     const int B4 = 32 * w + lane;
     tw4s[0 * kThreads + T] = __ldg(A.tw.tw9 + 2 * B4);  // zeta(9, 2 B4 + 1) = i * this one
@@ -94,6 +102,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_base_s;
+  buf_release(bs);  // the buffer starts out free
   const uint32_t tsp = tmem_base + ((uint32_t)((w & 3) * 32) << 16) + 128 * (w >> 2);  // rows 0..3
   const int P0 = 256 * w + lane;
   const PadAddr pa = pad_addr(work, T, w, lane);
@@ -134,9 +143,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
 #pragma unroll
           for (int m = 0; m < 8; m++) x[m] = make_double2(int_f64(nx[m]), int_f64(nx[m + 8]));
           if (rho + 1 < NR) load_row(rho + 1, nx);
-          fwd_pass1_store_p(x, pa);
+          fwd_pass1_store_p(x, pa, bs);
           __syncthreads();
-          fwd_warp_passes_p(pa, w, tw3, tw4, x);
+          fwd_warp_passes_p(pa, w, tw3, tw4, x, bs);
           if (rho < 4) {
             const double2 lo[4] = {x[0], x[1], x[2], x[3]};
             const double2 hi[4] = {x[4], x[5], x[6], x[7]};
@@ -146,7 +155,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
 #pragma unroll
             for (int j = 0; j < 8; j++) rows_s[(size_t)(rho - 4) * kM + P0 + 32 * j] = x[j];
           }
-          __syncthreads();  // `work` is reused by the next row
         }
         tm_wait_st();
       }
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
             }
           }
           PHASE_TICK(3);
-          inv_transform_p(cur, pa, w, tw3, tw4);
+          inv_transform_p(cur, pa, w, tw3, tw4, bs);
           PHASE_TICK(4);
 #pragma unroll
           for (int q = 0; q < 16; q++) {
@@ -230,10 +238,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  BufSync bs{smem_u32(tmem_base_s + 2), 0u};  // exchange-buffer mbarrier in the same 16-byte slot
+  if (T == 0) buf_init(bs.mbar);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_base_s;
+  buf_release(bs);  // the buffer starts out free
   // this thread's 128 columns: spectra rows at +0/+32/+64, twiddles at +96 (pass 3) / +112 (pass 4)
   const uint32_t tsp = tmem_base + ((uint32_t)((w & 3) * 32) << 16) + 128 * (w >> 2);
   const uint32_t ttw = tsp + 96;
@@ -358,16 +369,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
                 field_f64((__funnelshift_r((uint32_t)wb, (uint32_t)(wb >> 32), s1) >> s2) & 0x1ffffu, nb));
           }
           sgn = sg;
-          fwd_pass1_store_p(x, pa);
-          __syncthreads();
-          fwd_warp_passes_p(pa, w, tw3, tw4, x);
+          if (!(FHERAM_ABL & 4)) {
+            fwd_pass1_store_p(x, pa, bs);
+            __syncthreads();
+            fwd_warp_passes_p(pa, w, tw3, tw4, x, bs);
+          }
           {
             const double2 lo[4] = {x[0], x[1], x[2], x[3]};
             const double2 hi[4] = {x[4], x[5], x[6], x[7]};
             tm_st4(tsp + 32 * rho, lo);
             tm_st4(tsp + 32 * rho + 16, hi);
           }
-          __syncthreads();  // `work` is reused by the next row
         }
         tm_wait_st();
       }
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
             const double2* gp = G + ((size_t)rho * NOUT + o) * kM + P0;
             double2 g[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) g[j] = __ldg(gp + 32 * j);
+            for (int j = 0; j < 8; j++) g[j] = (FHERAM_ABL & 1) ? make_double2(1.0 + j, 0.5) : __ldg(gp + 32 * j);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
               double2 a[4];
@@ -404,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks3(const VmpArgs A) {
             }
           }
           PHASE_TICK(3);
-          inv_transform_p(cur, pa, w, tw3, tw4);
+          if (!(FHERAM_ABL & 2)) inv_transform_p(cur, pa, w, tw3, tw4, bs);
           PHASE_TICK(4);
           // cur[m] = phi_g(vmp)[T + 256 m] (+ i * [.. + 2048]); round and accumulate into the word
           if (l == 3) {

@@ -41,16 +41,49 @@ __device__ __forceinline__ PadAddr pad_addr(double2* work, int T, int w, int lan
 
 struct Tw4x { double2 a, b, c, d; };  // four twiddles of one pass
 
-// pass 1 on x[m] = z[T + 256 m]; result to the exchange buffer (block level)
-__device__ __forceinline__ void fwd_pass1_store_p(double2 (&x)[8], const PadAddr& p) {
+// Split barrier protecting the exchange buffer between transforms (write-after-read): a warp
+// RELEASES the buffer (one mbarrier arrival per warp) once it has read everything it needs, and a
+// thread ACQUIRES it (waits for the 8 arrivals of the previous transform) right before its first store
+// of the next transform -- hundreds to thousands of cycles later, so the wait is normally free.
+struct BufSync {
+  uint32_t mbar;   // shared-memory address of the mbarrier (8 bytes, 8-byte aligned)
+  uint32_t phase;  // parity of the phase the next acquire waits for
+};
+// one thread: init; then __syncthreads(); then every warp calls buf_release once (phase 0 completes)
+__device__ __forceinline__ void buf_init(uint32_t mbar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(mbar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void buf_release(const BufSync& b) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b.mbar) : "memory");
+}
+__device__ __forceinline__ void buf_acquire(BufSync& b) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(b.mbar), "r"(b.phase) : "memory");
+  b.phase ^= 1u;
+}
+
+// pass 1 on x[m] = z[T + 256 m]; result to the exchange buffer (block level); the caller issues
+// __syncthreads() before fwd_warp_passes_p
+__device__ __forceinline__ void fwd_pass1_store_p(double2 (&x)[8], const PadAddr& p, BufSync& bs) {
   radix8_fwd<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
+  buf_acquire(bs);
 #pragma unroll
   for (int m = 0; m < 8; m++) p.D[kBlk * m] = x[m];
 }
 // passes 2-4 of warp w after a block-level sync; returns the 8 final frequencies of this thread
 // (spectrum positions 256 w + 32 j + lane).  tw3() / tw4() deliver (a3,b3,c3,d3) / (b4a,b4b,c4a,c4b).
 template <typename F3, typename F4>
-__device__ __forceinline__ void fwd_warp_passes_p(const PadAddr& p, int w, F3&& tw3, F4&& tw4, double2 (&x)[8]) {
+__device__ __forceinline__ void fwd_warp_passes_p(const PadAddr& p, int w, F3&& tw3, F4&& tw4, double2 (&x)[8],
+                                                  const BufSync& bs) {
 #pragma unroll
   for (int m = 0; m < 8; m++) x[m] = p.A[36 * m];
   radix8_fwd<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
@@ -69,6 +102,7 @@ __device__ __forceinline__ void fwd_warp_passes_p(const PadAddr& p, int w, F3&& 
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; j++) x[j] = p.C[j];
+  buf_release(bs);
   {
     const Tw4x t = tw4();
     bf(x[0], x[2], t.a); bf(x[1], x[3], t.a); bf(x[4], x[6], t.b); bf(x[5], x[7], t.b);
@@ -76,16 +110,18 @@ __device__ __forceinline__ void fwd_warp_passes_p(const PadAddr& p, int w, F3&& 
     bf(x[4], x[5], t.d); bf(x[6], x[7], mul_i(t.d));
   }
 }
-// inverse: x[j] = this thread's 8 spectrum values; on return x[m] = M z[T + 256 m]
-// (two block barriers inside: the buffer may be reused right after the call)
+// inverse: x[j] = this thread's 8 spectrum values; on return x[m] = M z[T + 256 m].
+// Buffer protocol: buf_acquire() before the first store, buf_release() after the last load.
 template <typename F3, typename F4>
-__device__ __forceinline__ void inv_transform_p(double2 (&x)[8], const PadAddr& p, int w, F3&& tw3, F4&& tw4) {
+__device__ __forceinline__ void inv_transform_p(double2 (&x)[8], const PadAddr& p, int w, F3&& tw3, F4&& tw4,
+                                                BufSync& bs) {
   {
     const Tw4x t = tw4();
     ibf(x[0], x[1], t.c); ibf(x[2], x[3], mul_i(t.c));
     ibf(x[4], x[5], t.d); ibf(x[6], x[7], mul_i(t.d));
     ibf(x[0], x[2], t.a); ibf(x[1], x[3], t.a); ibf(x[4], x[6], t.b); ibf(x[5], x[7], t.b);
   }
+  buf_acquire(bs);
 #pragma unroll
   for (int j = 0; j < 8; j++) p.C[j] = x[j];
   __syncwarp();
@@ -107,7 +143,7 @@ __device__ __forceinline__ void inv_transform_p(double2 (&x)[8], const PadAddr& 
   __syncthreads();
 #pragma unroll
   for (int m = 0; m < 8; m++) x[m] = p.D[kBlk * m];
-  __syncthreads();
+  buf_release(bs);
   radix8_inv<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
 }
 
