@@ -17,6 +17,7 @@
 #include "kernels_ks2.cuh"
 #include "kernels_ks3.cuh"
 #include "kernels_ks4.cuh"
+#include "kernels_ks5.cuh"
 
 using namespace fheram;
 
@@ -215,6 +216,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
+  CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
+  CU(cudaFuncSetAttribute(k_ks5<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks4<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
   CU(cudaFuncSetAttribute(k_ks4<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
   CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
@@ -473,6 +476,11 @@ static VmpArgs base_args(fheram_ctx* c, int n_items, const int* src, int* dst, l
   for (int i = 0; i < kMaxSteps; i++) { a.gal[i] = 1; a.gal_inv[i] = 1; }
   a.tw = c->tw;
   a.phase_cycles = c->d_phase;
+  {
+    static int stagger = -1;
+    if (stagger < 0) { const char* e = getenv("FHERAM_STAGGER"); stagger = e ? atoi(e) : 0; }
+    a.stagger = stagger;
+  }
   return a;
 }
 static size_t prof_event(fheram_ctx* c) {
@@ -533,6 +541,28 @@ static int ks3_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FHERAM_KS3"); v = e ? atoi(e) : 1; }
   return v;
+}
+// one-operation-per-SM key-switch kernels (kernels_ks5.cuh): FHERAM_KS5 = 0 off, 1 narrow launches
+// (at most one item per SM) only, 2 every launch
+static int ks5_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KS5"); v = e ? atoi(e) : 1; }
+  return v;
+}
+template <typename K>
+static int launch_ks5(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
+  if (a.n_items <= 0) return 0;
+  int grid = a.n_items < c->sm_count ? a.n_items : c->sm_count;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
+  kernel<<<grid, kThreads5, kKs5Smem, c->stream>>>(a);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
 }
 // FHERAM_KSGEN=3 selects k_ks3 instead of the pipelined k_ks4 (kernels_ks4.cuh) where ks3_mode() applies
 static bool use_ks4() {
@@ -706,6 +736,7 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
   a.n_steps = n_dig;
   for (int s = 0; s < n_dig; s++) a.mat[s] = mats + (size_t)s * c->ggsw_prep_len();
   a.mat_div = mat_div; a.mat_stride = mat_stride;
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ext3, a, KC_EXT, kExt3Smem);  // forced (kernel-variant tests)
   if (use_split(c, n_items)) {
     // narrow launch: one step per launch, two CTAs per ciphertext (one output column each),
     // ping-pong between two temporaries because both CTAs read both input columns
@@ -749,6 +780,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
+  if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count)) return launch_ks5(c, k_ks5<MODE_TRACE>, a, KC_TRACE);
   if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
   if (use_split(c, n_items)) {
@@ -785,6 +817,8 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  // narrow two-sided combines are faster on the column-split k_vmp (31-33 us vs 37-39 us): k_ks5 only when forced
+  if (ks5_mode() == 2) return launch_ks5(c, k_ks5<MODE_COMBINE2>, a, KC_COMBINE2);
   if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
   if (use_split(c, n_items)) return launch_split(c, K_COMBINE2_S, a, smem_bytes(3, 1, true), KC_COMBINE2);

@@ -277,6 +277,7 @@ struct VmpArgs {
   // optional per-phase cycle counters (debug / DESIGN.md phase breakdown): gridDim.x * 8 slots
   // 0 prologue, 1 forward pass 1, 2 forward warp passes, 3 contraction, 4 inverse, 5 epilogue, 6 rest
   long long* phase_cycles;
+  int stagger;  // k_ks5: cycles by which group 1 trails group 0 after a CTA barrier (tuning knob)
 };
 #define PHASE_TICK(ph)                                                      \
   do {                                                                      \

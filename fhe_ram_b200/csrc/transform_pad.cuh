@@ -18,6 +18,13 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef FHERAM_ABL
+#define FHERAM_ABL 0
+#endif
+// timing ablations (results are garbage): 8 = no warp-local exchanges, 16 = no butterflies
+#define ABL_XCH if (!(FHERAM_ABL & 8))
+#define ABL_BFLY if (!(FHERAM_ABL & 16))
+
 namespace fheram {
 
 constexpr int kBlk = 288;            // padded slots per warp block
@@ -74,7 +81,7 @@ __device__ __forceinline__ void buf_acquire(BufSync& b) {
 // pass 1 on x[m] = z[T + 256 m]; result to the exchange buffer (block level); the caller issues
 // __syncthreads() before fwd_warp_passes_p
 __device__ __forceinline__ void fwd_pass1_store_p(double2 (&x)[8], const PadAddr& p, BufSync& bs) {
-  radix8_fwd<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
+  ABL_BFLY radix8_fwd<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
   buf_acquire(bs);
 #pragma unroll
   for (int m = 0; m < 8; m++) p.D[kBlk * m] = x[m];
@@ -86,28 +93,34 @@ __device__ __forceinline__ void fwd_warp_passes_p(const PadAddr& p, int w, F3&& 
                                                   const BufSync& bs) {
 #pragma unroll
   for (int m = 0; m < 8; m++) x[m] = p.A[36 * m];
-  radix8_fwd<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
+  ABL_BFLY radix8_fwd<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
+  ABL_XCH {
 #pragma unroll
-  for (int m = 0; m < 8; m++) p.A[36 * m] = x[m];
-  __syncwarp();
+    for (int m = 0; m < 8; m++) p.A[36 * m] = x[m];
+    __syncwarp();
 #pragma unroll
-  for (int m = 0; m < 8; m++) x[m] = p.B[4 * m];
+    for (int m = 0; m < 8; m++) x[m] = p.B[4 * m];
+  }
   {
     const Tw4x t = tw3();
-    radix8_fwd<true>(x, t.a, t.b, t.c, t.d);
+    ABL_BFLY radix8_fwd<true>(x, t.a, t.b, t.c, t.d);
   }
-  __syncwarp();
+  ABL_XCH {
+    __syncwarp();
 #pragma unroll
-  for (int m = 0; m < 8; m++) p.B[4 * m + (m >> 1)] = x[m];
-  __syncwarp();
+    for (int m = 0; m < 8; m++) p.B[4 * m + (m >> 1)] = x[m];
+    __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 8; j++) x[j] = p.C[j];
+    for (int j = 0; j < 8; j++) x[j] = p.C[j];
+  }
   buf_release(bs);
   {
     const Tw4x t = tw4();
-    bf(x[0], x[2], t.a); bf(x[1], x[3], t.a); bf(x[4], x[6], t.b); bf(x[5], x[7], t.b);
-    bf(x[0], x[1], t.c); bf(x[2], x[3], mul_i(t.c));
-    bf(x[4], x[5], t.d); bf(x[6], x[7], mul_i(t.d));
+    ABL_BFLY {
+      bf(x[0], x[2], t.a); bf(x[1], x[3], t.a); bf(x[4], x[6], t.b); bf(x[5], x[7], t.b);
+      bf(x[0], x[1], t.c); bf(x[2], x[3], mul_i(t.c));
+      bf(x[4], x[5], t.d); bf(x[6], x[7], mul_i(t.d));
+    }
   }
 }
 // inverse: x[j] = this thread's 8 spectrum values; on return x[m] = M z[T + 256 m].
@@ -117,34 +130,40 @@ __device__ __forceinline__ void inv_transform_p(double2 (&x)[8], const PadAddr& 
                                                 BufSync& bs) {
   {
     const Tw4x t = tw4();
-    ibf(x[0], x[1], t.c); ibf(x[2], x[3], mul_i(t.c));
-    ibf(x[4], x[5], t.d); ibf(x[6], x[7], mul_i(t.d));
-    ibf(x[0], x[2], t.a); ibf(x[1], x[3], t.a); ibf(x[4], x[6], t.b); ibf(x[5], x[7], t.b);
+    ABL_BFLY {
+      ibf(x[0], x[1], t.c); ibf(x[2], x[3], mul_i(t.c));
+      ibf(x[4], x[5], t.d); ibf(x[6], x[7], mul_i(t.d));
+      ibf(x[0], x[2], t.a); ibf(x[1], x[3], t.a); ibf(x[4], x[6], t.b); ibf(x[5], x[7], t.b);
+    }
   }
   buf_acquire(bs);
+  ABL_XCH {
 #pragma unroll
-  for (int j = 0; j < 8; j++) p.C[j] = x[j];
-  __syncwarp();
+    for (int j = 0; j < 8; j++) p.C[j] = x[j];
+    __syncwarp();
 #pragma unroll
-  for (int m = 0; m < 8; m++) x[m] = p.B[4 * m + (m >> 1)];
+    for (int m = 0; m < 8; m++) x[m] = p.B[4 * m + (m >> 1)];
+  }
   {
     const Tw4x t = tw3();
-    radix8_inv<true>(x, t.a, t.b, t.c, t.d);
+    ABL_BFLY radix8_inv<true>(x, t.a, t.b, t.c, t.d);
   }
-  __syncwarp();
+  ABL_XCH {
+    __syncwarp();
 #pragma unroll
-  for (int m = 0; m < 8; m++) p.B[4 * m] = x[m];
-  __syncwarp();
+    for (int m = 0; m < 8; m++) p.B[4 * m] = x[m];
+    __syncwarp();
 #pragma unroll
-  for (int m = 0; m < 8; m++) x[m] = p.A[36 * m];
-  radix8_inv<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
+    for (int m = 0; m < 8; m++) x[m] = p.A[36 * m];
+  }
+  ABL_BFLY radix8_inv<true>(x, c_tw_lo[8 + w], c_tw_lo[16 + 2 * w], c_tw_lo[32 + 4 * w], c_tw_lo[32 + 4 * w + 2]);
 #pragma unroll
   for (int m = 0; m < 8; m++) p.A[36 * m] = x[m];
   __syncthreads();
 #pragma unroll
   for (int m = 0; m < 8; m++) x[m] = p.D[kBlk * m];
   buf_release(bs);
-  radix8_inv<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
+  ABL_BFLY radix8_inv<true>(x, c_tw_lo[1], c_tw_lo[2], c_tw_lo[4], c_tw_lo[6]);
 }
 
 }  // namespace fheram

@@ -1,0 +1,43 @@
+"""Every kernel generation behind the same C ABI must give the same limbs as the oracle.
+
+The library picks a kernel per launch from the launch width (narrow: column-split k_vmp / k_ks5,
+wide: k_ext3 / k_ks4).  The small parity cases of test_gpu_parity.py only produce narrow launches, so
+each variant is forced through the whole limb-level parity set (external product, chains, trace,
+packer, read / read_prepare_write / write at four parameter sets, batched, sharded) in a
+subprocess: the selection knobs are read once per process.
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+SELECT = ("test_external_product_matches_oracle or test_external_product_adversarial_limbs or "
+          "test_coordinate_product_chain or test_trace_matches_oracle or test_packer_matches_oracle or "
+          "test_read_rpw_write_bit_exact or test_batched_reads_equal_single_reads or "
+          "test_sharded_stages_on_one_gpu")
+
+VARIANTS = {
+    # word-domain key switch, in-place accumulation + double-buffered tiles (k_ks4) and padded k_ext3
+    "ks4_ext3": {"FHERAM_KS3": "2", "FHERAM_KS5": "0"},
+    # word-domain key switch with register accumulators (k_ks3)
+    "ks3": {"FHERAM_KS3": "2", "FHERAM_KSGEN": "3", "FHERAM_KS5": "0"},
+    # one operation per SM, 512 threads, tiles parked in tensor memory (k_ks5), trace and combine
+    "ks5": {"FHERAM_KS5": "2"},
+    # digit-domain two-CTA kernels (k_ks2 / k_ext2) and the single-CTA k_vmp without column split
+    "ks2_vmp": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_SPLIT": "0"},
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_kernel_variant_is_bit_exact(built, name):
+    env = dict(os.environ)
+    env.update(VARIANTS[name])
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-m", "gpu",
+                        "-x", "-q", "-k", SELECT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, f"variant {name} {VARIANTS[name]}:\n{r.stdout[-3000:]}\n{r.stderr[-1000:]}"
+    assert " passed" in r.stdout
