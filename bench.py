@@ -406,21 +406,27 @@ def main():
     ach_tf = pd["ops"] * cls_flop[dom] / (pd["ms"] * 1e-3) / 1e12 if pd["ms"] > 0 else 0.0
     ach_gb = pd["ops"] * cls_bytes[dom] / (pd["ms"] * 1e-3) / 1e9 if pd["ms"] > 0 else 0.0
     shares = {k: round(prof[k]["ms"] / max(1e-9, sum(prof[c]["ms"] for c in prof)), 4) for k in prof}
-    traffic, traffic_src = None, None
+    traffic, traffic_src, l1tex_view = None, None, None
     try:  # DRAM bytes per op from the committed ncu --set full capture, scaled to this launch size
-        per_op = json.loads((ROOT / "profiles" / "ncu_dram_per_op.json").read_text())[dom]
+        captured = json.loads((ROOT / "profiles" / "ncu_dram_per_op.json").read_text())
+        per_op = captured[dom]
         traffic = per_op["dram_bytes_per_op"] * pd["ops"] / max(1, pd["launches"])
         traffic_src = per_op["capture"]
+        # the unit ncu shows closest to saturation (not a number measured in this run)
+        l1tex_view = {"unit": "l1tex data pipe (shared-memory exchanges + matrix loads)",
+                      "pct_of_peak_in_capture": captured["l1tex_data_pipe_pct"][dom], "source": per_op["capture"]}
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": f"k_vmp<{dom}>", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": {"ext": "k_ext3", "trace": "k_ks4<TRACE>", "combine2": "k_ks4<COMBINE2>"}[dom],
+        "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "fp64 FMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry; "
                        "nominal 37.2 TFLOP/s = 148 SM x 64 FMA x 2 x 1.965 GHz)",
         "avg_launch_ms": pd["ms"] / max(1, pd["launches"]), "launches": pd["launches"],
         "ops_per_launch": pd["ops"] / max(1, pd["launches"]), "flop_per_op": cls_flop[dom],
         "kernel_time_share": shares,
+        "l1tex_view": l1tex_view,
         "hbm_view": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach_gb / hbm_peak, "bytes_per_op": cls_bytes[dom],
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},

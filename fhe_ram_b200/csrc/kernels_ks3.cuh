@@ -132,9 +132,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
       {
         int nx[16];
         auto load_row = [&](int rho, int (&v)[16]) {
-          const int* p = xin + CT(rho & 1, rho >> 1);
+          // per-thread pointer made opaque: with a (uniform base + thread offset) split the compiler
+          // re-materialises the base in uniform registers for every access (two R2UR per load)
+          const int* p = xin + CT(rho & 1, rho >> 1) + T;
+          asm volatile("" : "+l"(p));
 #pragma unroll
-          for (int m = 0; m < 8; m++) { v[m] = p[T + 256 * m]; v[m + 8] = p[T + 256 * m + kM]; }
+          for (int m = 0; m < 8; m++) { v[m] = p[256 * m]; v[m + 8] = p[256 * m + kM]; }
         };
         load_row(0, nx);
 #pragma unroll 1
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
             const double2* gp = G + ((size_t)rho * NOUT + o) * kM + P0;
             double2 g[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) g[j] = __ldg(gp + 32 * j);
+            for (int j = 0; j < 8; j++) g[j] = ldg_pinned(gp + 32 * j);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
               double2 a[4];
@@ -197,15 +200,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
           PHASE_TICK(3);
           inv_transform_p(cur, pa, w, tw3, tw4, bs);
           PHASE_TICK(4);
+          int* dp = dst + CT(co, l < LRES ? l : 0) + T;
+          asm volatile("" : "+l"(dp));
 #pragma unroll
           for (int q = 0; q < 16; q++) {
-            const int i = T + 256 * (q & 7) + (q >> 3) * kM;
             const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
             const long long t = __double2ll_rn(v) + (long long)carry[q];
             const int c = (int)((t + 65536) >> kK);
             const int dg = (int)t - (c << kK);
             carry[q] = c;
-            if (l < LRES) dst[CT(co, l) + i] = dg;
+            if (l < LRES) dp[256 * (q & 7) + (q >> 3) * kM] = dg;
           }
           PHASE_TICK(5);
         }
