@@ -85,6 +85,9 @@ SIGNATURES = {
     "fheram_address_alloc": (C.c_int, [_V, C.c_int, _PV]),
     "fheram_address_raw_ptr": (_V, [_V]),
     "fheram_address_upload_slice": (C.c_int, [_V, _P64, C.c_int, C.c_int]),
+    "fheram_address_upload_slice_async": (C.c_int, [_V, _P64, C.c_int, C.c_int]),
+    "fheram_address_wait_upload": (C.c_int, [_V]),
+    "fheram_address_release": (C.c_int, [_V]),
     "fheram_address_prepare": (C.c_int, [_V]),
     "fheram_address_count": (C.c_int, [_V]),
     "fheram_address_destroy": (C.c_int, [_V]),
@@ -405,6 +408,17 @@ class Address:
     def upload_slice(self, limbs: np.ndarray, first: int, count: int):
         _check(lib().fheram_address_upload_slice(self.h, _p(np.ascontiguousarray(limbs, dtype=np.int64).reshape(-1)),
                                                  first, count))
+
+    def upload_slice_async(self, limbs: np.ndarray, first: int, count: int):
+        """limbs must stay alive (and should be pinned: host_register) until wait_upload's stream work ran"""
+        assert limbs.dtype == np.int64 and limbs.flags.c_contiguous
+        _check(lib().fheram_address_upload_slice_async(self.h, _p(limbs.reshape(-1)), first, count))
+
+    def wait_upload(self):
+        _check(lib().fheram_address_wait_upload(self.h))
+
+    def release(self):
+        _check(lib().fheram_address_release(self.h))
 
     def raw_ptr(self) -> int:
         return int(lib().fheram_address_raw_ptr(self.h))

@@ -162,6 +162,7 @@ struct fheram_ctx {
   int device = 0, sm_count = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
   double2* d_tw = nullptr;  // tw6 | tw7c | tw8c | tw9 | tw10c
   Twiddles tw;
   int* d_err = nullptr;
@@ -307,6 +308,7 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
   cudaFree(c->d_tw); cudaFree(c->d_err);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -666,6 +668,11 @@ struct fheram_address {
   int* inv_raw = nullptr;    // [n_ggsw] GGSW(X^+digit), built lazily by write
   double2* inv_prep = nullptr;
   bool inv_ready = false;
+  // asynchronous slice upload (multi-GPU host-buffer pipeline): int64 staging, copy-stream events
+  long long* stage = nullptr;
+  size_t stage_cap = 0;
+  cudaEvent_t uploaded = nullptr, released = nullptr;
+  bool released_valid = false;
 };
 
 extern "C" int fheram_address_load_batch(fheram_ctx* c, const int64_t* ggsw, int n, fheram_address** out) {
@@ -705,6 +712,47 @@ extern "C" int fheram_address_upload_slice(fheram_address* a, const int64_t* ggs
   const size_t per = (size_t)c->d.n_ggsw * c->ggsw_raw_len();
   return upload_i64(c, ggsw, (size_t)count * per, a->raw + (size_t)first * per);
 }
+// Asynchronous variant for pipelines: host -> device copy and int64 -> int32 conversion run on the
+// context's copy stream; fheram_address_wait_upload makes the compute stream wait for them, and
+// fheram_address_release (recorded on the compute stream once the reads that use this address set
+// have been issued) lets the next upload into the same set start as soon as they are done.
+extern "C" int fheram_address_upload_slice_async(fheram_address* a, const int64_t* ggsw, int first, int count) {
+  if (!a || !ggsw || first < 0 || count < 1 || first + count > a->count) return fail(FHERAM_ERR_INVALID, "bad slice");
+  fheram_ctx* c = a->c;
+  CU(cudaSetDevice(c->device));
+  if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  const size_t per = (size_t)c->d.n_ggsw * c->ggsw_raw_len();
+  const size_t n = (size_t)count * per;
+  if (a->stage_cap < n) {
+    CU(cudaStreamSynchronize(c->copy_stream));
+    cudaFree(a->stage);
+    a->stage = nullptr; a->stage_cap = 0;
+    CU(cudaMalloc(&a->stage, sizeof(long long) * n));
+    a->stage_cap = n;
+  }
+  if (!a->uploaded) CU(cudaEventCreateWithFlags(&a->uploaded, cudaEventDisableTiming));
+  if (a->released_valid) CU(cudaStreamWaitEvent(c->copy_stream, a->released, 0));
+  CU(cudaMemcpyAsync(a->stage, ggsw, sizeof(long long) * n, cudaMemcpyHostToDevice, c->copy_stream));
+  k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->copy_stream>>>(a->stage, a->raw + (size_t)first * per, n, c->d_err);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(a->uploaded, c->copy_stream));
+  return 0;
+}
+extern "C" int fheram_address_wait_upload(fheram_address* a) {
+  if (!a || !a->uploaded) return fail(FHERAM_ERR_INVALID, "no upload in flight");
+  CU(cudaSetDevice(a->c->device));
+  CU(cudaStreamWaitEvent(a->c->stream, a->uploaded, 0));
+  return 0;
+}
+extern "C" int fheram_address_release(fheram_address* a) {
+  if (!a) return fail(FHERAM_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(a->c->device));
+  if (!a->released) CU(cudaEventCreateWithFlags(&a->released, cudaEventDisableTiming));
+  CU(cudaEventRecord(a->released, a->c->stream));
+  a->released_valid = true;
+  return 0;
+}
 extern "C" int fheram_address_prepare(fheram_address* a) {  // CoordinatePrepared::prepare for every address
   if (!a) return fail(FHERAM_ERR_INVALID, "null argument");
   fheram_ctx* c = a->c;
@@ -719,7 +767,10 @@ extern "C" int fheram_address_count(const fheram_address* a) { return a ? a->cou
 extern "C" int fheram_address_destroy(fheram_address* a) {
   if (!a) return 0;
   cudaSetDevice(a->c->device);
-  cudaFree(a->raw); cudaFree(a->prep); cudaFree(a->inv_raw); cudaFree(a->inv_prep);
+  if (a->c->copy_stream) cudaStreamSynchronize(a->c->copy_stream);
+  cudaFree(a->raw); cudaFree(a->prep); cudaFree(a->inv_raw); cudaFree(a->inv_prep); cudaFree(a->stage);
+  if (a->uploaded) cudaEventDestroy(a->uploaded);
+  if (a->released) cudaEventDestroy(a->released);
   delete a;
   return 0;
 }

@@ -147,20 +147,48 @@ class ShardedRam:
         G, rank = self.world, self.rank
         per = params.n_ggsw() * params.ggsw_len()          # int32 limbs per address on the device
 
+        # host-buffer path, pipelined in chunks of `chunk` reads per rank: every rank uploads only its own
+        # addresses over PCIe on a copy stream (the others arrive over NVLink with one all-gather per
+        # chunk), so the upload of chunk k+1 overlaps prepare / read / exchange / finish of chunk k
+        chunk = max(1, min(64, B // G))
+        n_chunks = (B // G + chunk - 1) // chunk
+        sets = [api.Address.device_alloc(params, chunk * G) for _ in range(2)]
+        L = params.word_size() * params.glwe_len()
+
         def run_e2e():
-            # every rank uploads only its own B/G addresses over PCIe; the others arrive over NVLink
-            a = api.Address.device_alloc(params, B)
             cnt = B // G
-            a.upload_slice(addr_limbs[rank * cnt:(rank + 1) * cnt], rank * cnt, cnt)
-            if G > 1:
-                full = torch.as_tensor(_DevView(a.raw_ptr(), B * per), device=f"cuda:{params.device}")
-                dist.all_gather_into_tensor(full, full[rank * cnt * per:(rank + 1) * cnt * per])
-            a.prepare()
-            mine = self.read_batch_local_slice(a, keys)
-            n = mine.numel() // (params.word_size() * params.glwe_len()) * params.word_size()
-            api._check(api.lib().fheram_download_glwe(params.module(), C.c_void_p(mine.data_ptr()), n,
-                                                      api._p(out_host)))
-            a.close()
+
+            def issue_upload(ci):
+                a = sets[ci & 1]
+                b0 = rank * cnt + ci * chunk
+                nb = min(chunk, cnt - ci * chunk)
+                # chunk layout on the device: [G ranks][chunk] so that one all-gather completes it
+                a.upload_slice_async(addr_limbs[b0:b0 + nb], rank * chunk, nb)
+
+            issue_upload(0)
+            for ci in range(n_chunks):
+                if ci + 1 < n_chunks:
+                    issue_upload(ci + 1)
+                a = sets[ci & 1]
+                nb = min(chunk, cnt - ci * chunk)
+                a.wait_upload()
+                if G > 1:
+                    full = torch.as_tensor(_DevView(a.raw_ptr(), G * chunk * per), device=f"cuda:{params.device}")
+                    dist.all_gather_into_tensor(full, full[rank * chunk * per:(rank + 1) * chunk * per])
+                a.prepare()
+                # the chunk holds G*chunk addresses, [r][j] = read (r*cnt + ci*chunk + j): this rank finishes
+                # the `chunk` reads of its own row
+                part = self.e.read_local(a, keys)                      # [G*chunk][ws] local partials
+                if G > 1:
+                    recv = self.e.empty(part.numel())
+                    dist.all_to_all_single(recv, part)
+                else:
+                    recv = part
+                mine = self.e.read_finish(recv, chunk, a, rank * chunk, keys)
+                a.release()
+                api._check(api.lib().fheram_download_glwe(params.module(), C.c_void_p(mine.data_ptr()),
+                                                          nb * params.word_size(),
+                                                          api._p(out_host[ci * chunk:ci * chunk + nb])))
             return out_host
 
         return run_resident, run_e2e

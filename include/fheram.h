@@ -124,6 +124,13 @@ int fheram_address_alloc(fheram_ctx *ctx, int n, fheram_address **out);
 int32_t *fheram_address_raw_ptr(fheram_address *a);
 int fheram_address_upload_slice(fheram_address *a, const int64_t *ggsw, int first, int count);
 int fheram_address_prepare(fheram_address *a);
+/* pipelined variant: the copy (from pinned / registered host memory) and the int64 -> int32 conversion run
+ * on a copy stream; _wait_upload orders the compute stream after them; _release is recorded on the compute
+ * stream after the last use of this address set so that the next _upload_slice_async into it may start.
+ * A limb outside +-2^30 is reported by the next synchronous call (error flag on the device). */
+int fheram_address_upload_slice_async(fheram_address *a, const int64_t *ggsw, int first, int count);
+int fheram_address_wait_upload(fheram_address *a);
+int fheram_address_release(fheram_address *a);
 int fheram_address_count(const fheram_address *a);
 int fheram_address_destroy(fheram_address *a);
 
