@@ -58,6 +58,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None   # timed window (time.time()); rows carry their arrival time
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -70,11 +77,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        # samples taken inside the timed window; a window shorter than the sampling period falls back to
+        # the samples of the warm-up + timed span (same kernels, same load) and says so
+        window = "timed region"
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.05)]
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than the sampling period)"
+        self.rows = rows
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -84,7 +98,7 @@ class ClockSampler:
                     reasons.add(nm)
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_addresses(fr, params, sk, idxs, threads):
@@ -276,14 +290,16 @@ def main():
         return ms
 
     # ---- warm-up, then the device-resident timed region --------------------------------
+    sampler = ClockSampler(device)
+    sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             run_resident()
-    sampler = ClockSampler(device)
-    sampler.start()
     params.profile(True)
     l0 = params.launch_count()
+    sampler.mark_start()
     ms_total = timed(run_resident, args.steps)
+    sampler.mark_end()
     launches = params.launch_count() - l0
     prof = params.profile_get()
     params.profile(False)

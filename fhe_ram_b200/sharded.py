@@ -150,7 +150,7 @@ class ShardedRam:
         # host-buffer path, pipelined in chunks of `chunk` reads per rank: every rank uploads only its own
         # addresses over PCIe on a copy stream (the others arrive over NVLink with one all-gather per
         # chunk), so the upload of chunk k+1 overlaps prepare / read / exchange / finish of chunk k
-        chunk = max(1, min(64, B // G))
+        chunk = max(1, min(64, max(16, B // G // 4), B // G))  # at least four pipeline stages when the slice allows
         n_chunks = (B // G + chunk - 1) // chunk
         sets = [api.Address.device_alloc(params, chunk * G) for _ in range(2)]
         L = params.word_size() * params.glwe_len()
