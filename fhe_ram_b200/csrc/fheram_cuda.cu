@@ -285,6 +285,13 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   // odd entry (k_ext3) agree exactly with those that load it
   for (int b = 1; b < 512; b += 2) q[b - 512] = make_double2(-q[b - 513].y, q[b - 513].x);
   for (int b = 0; b < 512; b++) zeta(10, 2 * b, q++);
+  // zeta(10, 4k+2) = e^(i pi/4) zeta(10, 4k): same treatment, with the roundings of mul_e8 (kernels_ks3.cuh)
+  for (int b = 1; b < 512; b += 2) {
+    const double2 w = q[b - 513];
+    const volatile double dx = w.x - w.y, sx = w.x + w.y;
+    const double r = 0.70710678118654757;
+    q[b - 512] = make_double2(dx * r, sx * r);
+  }
   CU(cudaMemcpyToSymbol(c_tw_lo, lo.data(), sizeof(double2) * 64));
   CU(cudaMemcpyToSymbol(c_tw3, hi.data(), sizeof(double2) * 256));  // tw6 | tw7c | tw8c
   CU(cudaMalloc(&c->d_tw, sizeof(double2) * hi.size()));
@@ -916,8 +923,9 @@ struct fheram_ram {
   struct HostPipe {          // fheram_ram_read_batch_host: double-buffered upload pipeline
     struct Set { long long* stage = nullptr; fheram_address a; cudaEvent_t copied = nullptr, freed = nullptr; };
     Set sets[2];
-    long long* out_stage = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    long long* out_stage[2] = {nullptr, nullptr};
+    cudaEvent_t out_ready[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr, down_stream = nullptr;
     int cap = 0;
   } pipe;
 };
@@ -961,8 +969,13 @@ extern "C" int fheram_ram_destroy(fheram_ram* r) {
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.freed) cudaEventDestroy(s.freed);
   }
-  cudaFree(r->pipe.out_stage);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(r->pipe.out_stage[i]);
+    if (r->pipe.out_ready[i]) cudaEventDestroy(r->pipe.out_ready[i]);
+    if (r->pipe.out_done[i]) cudaEventDestroy(r->pipe.out_done[i]);
+  }
   if (r->pipe.copy_stream) cudaStreamDestroy(r->pipe.copy_stream);
+  if (r->pipe.down_stream) cudaStreamDestroy(r->pipe.down_stream);
   delete r;
   return 0;
 }
@@ -1207,10 +1220,12 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
   auto cleanup = [&]() {
     cudaStreamSynchronize(hp.copy_stream);
     cudaStreamSynchronize(c->stream);
+    if (hp.down_stream) cudaStreamSynchronize(hp.down_stream);
   };
 #define TRYC(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define CUC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   if (!hp.copy_stream) CU(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
+  if (!hp.down_stream) CU(cudaStreamCreateWithFlags(&hp.down_stream, cudaStreamNonBlocking));
   if (hp.cap < chunk) {
     for (auto& s : hp.sets) {
       cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
@@ -1222,13 +1237,16 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
       if (!s.copied) CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
       if (!s.freed) CU(cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming));
     }
-    cudaFree(hp.out_stage);
-    hp.out_stage = nullptr;
-    CU(cudaMalloc(&hp.out_stage, sizeof(long long) * (size_t)chunk * ws * L));
+    for (int i = 0; i < 2; i++) {
+      cudaFree(hp.out_stage[i]);
+      hp.out_stage[i] = nullptr;
+      CU(cudaMalloc(&hp.out_stage[i], sizeof(long long) * (size_t)chunk * ws * L));
+      if (!hp.out_ready[i]) CU(cudaEventCreateWithFlags(&hp.out_ready[i], cudaEventDisableTiming));
+      if (!hp.out_done[i]) CU(cudaEventCreateWithFlags(&hp.out_done[i], cudaEventDisableTiming));
+    }
     hp.cap = chunk;
   }
   Set* sets = hp.sets;
-  long long* out_stage = hp.out_stage;
   cudaStream_t copy_stream = hp.copy_stream;
   const int n_chunks = (n + chunk - 1) / chunk;
   auto issue_copy = [&](int ci) -> int {
@@ -1253,12 +1271,19 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
     TRYC(ram_local_stage(r, &s.a, 0, nb, k, false));
     TRYC(ram_finish_stage(r, (const int*)r->partial.p, nb, 0, nb, &s.a, 0, k, false));
     CUC(cudaEventRecord(s.freed, c->stream));
-    k_i32_to_i64<<<c->sm_count * 4, 256, 0, c->stream>>>((const int*)r->result.p, out_stage, (size_t)nb * ws * L);
+    // results: widen on the compute stream, download on a third stream (overlaps the next chunk's reads)
+    long long* os = hp.out_stage[ci & 1];
+    if (ci >= 2) CUC(cudaStreamWaitEvent(c->stream, hp.out_done[ci & 1], 0));
+    k_i32_to_i64<<<c->sm_count * 4, 256, 0, c->stream>>>((const int*)r->result.p, os, (size_t)nb * ws * L);
     c->launches++;
-    CUC(cudaMemcpyAsync(out_host + (size_t)b0 * ws * L, out_stage, sizeof(long long) * (size_t)nb * ws * L,
-                        cudaMemcpyDeviceToHost, c->stream));
+    CUC(cudaEventRecord(hp.out_ready[ci & 1], c->stream));
+    CUC(cudaStreamWaitEvent(hp.down_stream, hp.out_ready[ci & 1], 0));
+    CUC(cudaMemcpyAsync(out_host + (size_t)b0 * ws * L, os, sizeof(long long) * (size_t)nb * ws * L,
+                        cudaMemcpyDeviceToHost, hp.down_stream));
+    CUC(cudaEventRecord(hp.out_done[ci & 1], hp.down_stream));
   }
   CUC(cudaStreamSynchronize(c->stream));
+  CUC(cudaStreamSynchronize(hp.down_stream));
   int err = 0;
   CUC(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   cleanup();

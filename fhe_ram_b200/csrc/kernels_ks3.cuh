@@ -71,17 +71,24 @@ __device__ __forceinline__ double int_f64(int v) {
   return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;
 }
 
-// 36 (padded exchange buffer) + 64 (two spectra) + 12 (pass-4 twiddles b4a, c4a, c4b; b4b = i b4a) = 112 KiB
+// 36 (padded exchange buffer) + 64 (two spectra) + 8 (pass-4 twiddles b4a, c4a; b4b = i b4a, c4b = e^(i pi/4) c4a)
+// + 4 (pass-3 twiddle table) = 112 KiB
 constexpr size_t kExt3Smem = (size_t)kWorkPad * sizeof(double2) + (size_t)2 * kM * sizeof(double2) +
                              (size_t)3 * kThreads * sizeof(double2) + 16;
+// w * e^(i pi/4), with exactly the roundings the host uses to build the odd entries of tw10c
+__device__ __forceinline__ double2 mul_e8(double2 w) {
+  const double r = 0.70710678118654757;
+  return make_double2(__dmul_rn(__dadd_rn(w.x, -w.y), r), __dmul_rn(__dadd_rn(w.x, w.y), r));
+}
 
 __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
   constexpr int NR = 6, LOUT = 4, LRES = 3, NOUT = 2 * LOUT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* work = reinterpret_cast<double2*>(smem_raw);
   double2* rows_s = work + kWorkPad;           // spectra of rows 4 and 5
-  double2* tw4s = rows_s + 2 * kM;             // [3][256] pass-4 twiddles, thread-private columns
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tw4s + 3 * kThreads);
+  double2* tw4s = rows_s + 2 * kM;             // [2][256] pass-4 twiddles b4a, c4a (thread-private columns)
+  double2* tw3s = tw4s + 2 * kThreads;         // [256] pass-3 twiddle table zeta(6,B) | zeta(7,2B) | zeta(8,2k)
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tw3s + kThreads);
 
   const int T = threadIdx.x, w = T >> 5, lane = T & 31;
   auto CT = [](int col, int limb) { return (limb * 2 + col) * kN; };
@@ -94,9 +101,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
   if (T == 0) buf_init(bs.mbar);
   {
     const int B4 = 32 * w + lane;
-    tw4s[0 * kThreads + T] = __ldg(A.tw.tw9 + 2 * B4);  // zeta(9, 2 B4 + 1) = i * this one
-    tw4s[1 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4);
-    tw4s[2 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4 + 1);
+    tw4s[0 * kThreads + T] = __ldg(A.tw.tw9 + 2 * B4);    // zeta(9, 2 B4 + 1) = i * this one
+    tw4s[1 * kThreads + T] = __ldg(A.tw.tw10c + 2 * B4);  // zeta(10, 4 B4 + 2) = e^(i pi/4) * this one
+    tw3s[T] = __ldg(A.tw.tw6 + T);                        // tw6 | tw7c | tw8c are contiguous
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -106,10 +113,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext3(const VmpArgs A) {
   const uint32_t tsp = tmem_base + ((uint32_t)((w & 3) * 32) << 16) + 128 * (w >> 2);  // rows 0..3
   const int P0 = 256 * w + lane;
   const PadAddr pa = pad_addr(work, T, w, lane);
-  auto tw3 = [&]() { const Tw3 t = load_tw3(w, lane); return Tw4x{t.a, t.b, t.c, t.d}; };
+  // pass-3 twiddles from a 4 KiB shared table (8 distinct entries per warp, broadcast within quads):
+  // k_ext2 read them from the constant bank, where 8 distinct addresses per warp serialise in the
+  // address-divergence unit (ncu: ADU pipe 37 %)
+  auto tw3 = [&]() {
+    const int B = 8 * w + (lane >> 2);
+    return Tw4x{tw3s[B], tw3s[64 + B], tw3s[128 + 2 * B], tw3s[128 + 2 * B + 1]};
+  };
   auto tw4 = [&]() {
-    const double2 b4a = tw4s[T];
-    return Tw4x{b4a, mul_i(b4a), tw4s[kThreads + T], tw4s[2 * kThreads + T]};
+    const double2 b4a = tw4s[T], c4a = tw4s[kThreads + T];
+    return Tw4x{b4a, mul_i(b4a), c4a, mul_e8(c4a)};
   };
   long long phase_t0 = A.phase_cycles ? clock64() : 0;
 
