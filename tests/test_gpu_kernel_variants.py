@@ -17,6 +17,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 SELECT = ("test_external_product_matches_oracle or test_external_product_adversarial_limbs or "
           "test_coordinate_product_chain or test_trace_matches_oracle or test_packer_matches_oracle or "
+          "test_trace_adversarial_limbs or test_packer_adversarial_limbs or "
           "test_read_rpw_write_bit_exact or test_batched_reads_equal_single_reads or "
           "test_sharded_stages_on_one_gpu")
 

@@ -79,6 +79,47 @@ def test_trace_matches_oracle(scenario, gpu_keys):
     assert np.array_equal(got[0], s.orc.trace(s.okeys, cts[0], 3, 9))
 
 
+def _extreme_glwe(rng, params, n):
+    """ciphertexts whose digits sit on the edges of the balanced range: the word-domain kernels
+    (kernels_ks3.cuh) replace digit carry chains by arithmetic mod 2^51 on biased words, so the cases to
+    pin are -2^16 (whose negation under a rotation / automorphism is the non-canonical +2^16), 2^16 - 1,
+    and values whose top digit wraps"""
+    L = params.glwe_len()
+    cts = np.empty((n, L), dtype=np.int64)
+    cts[0, :] = -(1 << 16)
+    cts[1 % n, :] = (1 << 16) - 1
+    for i in range(2, n):
+        cts[i] = rng.choice(np.array([-(1 << 16), -(1 << 16) + 1, -1, 0, 1, (1 << 16) - 2, (1 << 16) - 1], dtype=np.int64), size=L)
+    return cts
+
+
+def test_trace_adversarial_limbs(scenario, gpu_keys):
+    from fhe_ram_b200 import api
+    s = scenario()
+    keys = gpu_keys(s)
+    cts = _extreme_glwe(np.random.default_rng(15), s.params, 4)
+    got = api.glwe_trace(s.params, keys, cts)
+    for i in range(4):
+        want = s.orc.trace(s.okeys, cts[i])
+        assert np.array_equal(got[i], want), (i, np.count_nonzero(got[i] != want))
+
+
+def test_packer_adversarial_limbs(scenario, gpu_keys):
+    from fhe_ram_b200 import api
+    s = scenario()
+    keys = gpu_keys(s)
+    n = 4
+    cts = _extreme_glwe(np.random.default_rng(16), s.params, n)
+    got = api.glwe_pack(s.params, keys, cts)
+    N, log_n = s.params.n(), s.params.log_n()
+    feed = []
+    for j in range(N):
+        jr = int(format(j, f"0{log_n}b")[::-1], 2)
+        feed.append(cts[jr] if jr < n else None)
+    want = s.orc.pack(s.okeys, feed)
+    assert np.array_equal(got, want), np.count_nonzero(got != want)
+
+
 @pytest.mark.parametrize("n", [1, 2, 8])
 def test_packer_matches_oracle(scenario, gpu_keys, n):
     """GLWEPacker fed as src/ram.rs:424-449 does (bit-reversed order, None elsewhere)."""
