@@ -290,6 +290,29 @@ def test_full_size_2pow18_properties(scenario, gpu_keys):
     ram.close()
 
 
+def test_wide_kernels_repeatable_and_equal_to_narrow(scenario, gpu_keys):
+    """2^18 x 4 B: a batch (wide launches: k_ext3 / k_ks4, two CTAs per SM, split barriers, in-place word
+    accumulation) must give, limb for limb, what single reads (narrow launches: k_vmp split / k_ks5) give, and the
+    same limbs on every repetition (compute-sanitizer is not available on the GPU pool: races would show up here)."""
+    s = scenario(1 << 18, 4, 9)
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    idxs = [3, 4097, 77777, (1 << 18) - 2]
+    addrs = [s.address(i) for i in idxs]
+    batch = fr.Address.batch(p, addrs)
+    first = ram.read_batch(batch, keys)
+    for _ in range(4):
+        again = ram.read_batch(batch, keys)
+        assert np.array_equal(first, again), np.count_nonzero(first != again)
+    for b, a in enumerate(addrs):
+        single = ram.read(a, keys)
+        assert np.array_equal(single, first[b]), (b, np.count_nonzero(single != first[b]))
+        s.check_decrypt(first[b], idxs[b])
+    ram.close()
+
+
 @pytest.mark.parametrize("n_shards", [2, 4])
 def test_sharded_stages_on_one_gpu(scenario, gpu_keys, n_shards):
     """The sharded path of the C ABI with every shard emulated on one GPU: local
