@@ -37,7 +37,18 @@ extern "C" {
                                out: *mut *mut fheram_keys) -> c_int;
     pub fn fheram_keys_destroy(k: *mut fheram_keys) -> c_int;
     pub fn fheram_address_load(c: *mut fheram_ctx, ggsw: *const i64, out: *mut *mut fheram_address) -> c_int;
+    pub fn fheram_address_load_batch(c: *mut fheram_ctx, ggsw: *const i64, n: c_int, out: *mut *mut fheram_address) -> c_int;
     pub fn fheram_address_destroy(a: *mut fheram_address) -> c_int;
+    // batched reads on one resident RAM (BASELINE config 3); `_host` pipelines upload / prepare / read / download
+    pub fn fheram_ram_read_batch(r: *mut fheram_ram, a: *const fheram_address, k: *const fheram_keys, out: *mut i64) -> c_int;
+    pub fn fheram_ram_read_batch_host(r: *mut fheram_ram, ggsw_host: *const i64, n: c_int, k: *const fheram_keys,
+                                      out_host: *mut i64) -> c_int;
+    // multi-GPU building blocks (one process per GPU): each rank uploads 1/G of a batch and all-gathers the rest
+    pub fn fheram_address_alloc(c: *mut fheram_ctx, n: c_int, out: *mut *mut fheram_address) -> c_int;
+    pub fn fheram_address_upload_slice_async(a: *mut fheram_address, ggsw: *const i64, first: c_int, count: c_int) -> c_int;
+    pub fn fheram_address_wait_upload(a: *mut fheram_address) -> c_int;
+    pub fn fheram_address_release(a: *mut fheram_address) -> c_int;
+    pub fn fheram_address_prepare(a: *mut fheram_address) -> c_int;
     pub fn fheram_ram_create(c: *mut fheram_ctx, out: *mut *mut fheram_ram) -> c_int;
     pub fn fheram_ram_destroy(r: *mut fheram_ram) -> c_int;
     pub fn fheram_ram_load(r: *mut fheram_ram, cts: *const i64) -> c_int;
