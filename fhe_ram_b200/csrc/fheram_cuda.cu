@@ -18,6 +18,7 @@
 #include "kernels_ks3.cuh"
 #include "kernels_ks4.cuh"
 #include "kernels_ks5.cuh"
+#include "kernels_ks6.cuh"
 
 using namespace fheram;
 
@@ -217,6 +218,7 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
+  CU(cudaFuncSetAttribute(k_ks6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks4<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
@@ -573,6 +575,25 @@ static int launch_ks5(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   CU(cudaGetLastError());
   return 0;
 }
+// two-CTA-cluster trace kernel (kernels_ks6.cuh) for launches of at most sm_count / 2 chains; FHERAM_KS6=0 disables
+static bool use_ks6(const fheram_ctx* c, int n_items) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KS6"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && 2 * n_items <= c->sm_count;
+}
+static int launch_ks6(fheram_ctx* c, const VmpArgs& a) {
+  if (a.n_items <= 0) return 0;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
+  k_ks6<<<2 * a.n_items, kThreads5, kKs5Smem, c->stream>>>(a);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({KC_TRACE, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
 // FHERAM_KSGEN=3 selects k_ks3 instead of the pipelined k_ks4 (kernels_ks4.cuh) where ks3_mode() applies
 static bool use_ks4() {
   static int v = -1;
@@ -838,6 +859,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
+  if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, a);
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count)) return launch_ks5(c, k_ks5<MODE_TRACE>, a, KC_TRACE);
   if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);

@@ -27,7 +27,7 @@ VARIANTS = {
     # word-domain key switch with register accumulators (k_ks3)
     "ks3": {"FHERAM_KS3": "2", "FHERAM_KSGEN": "3", "FHERAM_KS5": "0"},
     # one operation per SM, 512 threads, tiles parked in tensor memory (k_ks5), trace and combine
-    "ks5": {"FHERAM_KS5": "2"},
+    "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0"},
     # digit-domain two-CTA kernels (k_ks2 / k_ext2) and the single-CTA k_vmp without column split
     "ks2_vmp": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_SPLIT": "0"},
 }
