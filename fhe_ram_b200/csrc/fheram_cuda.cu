@@ -218,7 +218,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
-  CU(cudaFuncSetAttribute(k_ks6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
+  CU(cudaFuncSetAttribute(k_ks6<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
+  CU(cudaFuncSetAttribute(k_ks6<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks4<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
@@ -581,14 +582,15 @@ static bool use_ks6(const fheram_ctx* c, int n_items) {
   if (v < 0) { const char* e = getenv("FHERAM_KS6"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1 && 2 * n_items <= c->sm_count;
 }
-static int launch_ks6(fheram_ctx* c, const VmpArgs& a) {
+template <typename K>
+static int launch_ks6(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   if (a.n_items <= 0) return 0;
   size_t e0 = 0;
   if (c->profile) e0 = prof_event(c);
-  k_ks6<<<2 * a.n_items, kThreads5, kKs5Smem, c->stream>>>(a);
+  kernel<<<2 * a.n_items, kThreads5, kKs5Smem, c->stream>>>(a);
   if (c->profile) {
     size_t e1 = prof_event(c);
-    c->ev_recs.push_back({KC_TRACE, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
   }
   c->launches++;
   CU(cudaGetLastError());
@@ -859,7 +861,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
-  if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, a);
+  if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, k_ks6<MODE_TRACE>, a, KC_TRACE);
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count)) return launch_ks5(c, k_ks5<MODE_TRACE>, a, KC_TRACE);
   if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
@@ -897,8 +899,10 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
-  // narrow two-sided combines are faster on the column-split k_vmp (31-33 us vs 37-39 us): k_ks5 only when forced
-  if (ks5_mode() == 2) return launch_ks5(c, k_ks5<MODE_COMBINE2>, a, KC_COMBINE2);
+  if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, k_ks6<MODE_COMBINE2>, a, KC_COMBINE2);
+  // one item per SM where two CTAs per item no longer fit (75 .. sm_count items): 37-39 us against 45 us of k_vmp
+  if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count && 2 * n_items > c->sm_count))
+    return launch_ks5(c, k_ks5<MODE_COMBINE2>, a, KC_COMBINE2);
   if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
   if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
   if (use_split(c, n_items)) return launch_split(c, K_COMBINE2_S, a, smem_bytes(3, 1, true), KC_COMBINE2);

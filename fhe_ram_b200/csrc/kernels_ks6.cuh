@@ -35,7 +35,9 @@ __device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long
   asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(const VmpArgs A) {
+  static_assert(MODE == MODE_TRACE || MODE == MODE_COMBINE2, "key-switch modes only");
   constexpr int LOUT = 4, NOUT = 2 * LOUT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* work_all = reinterpret_cast<double2*>(smem_raw);                         // [2 groups] exchange buffers
@@ -76,8 +78,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
   const PadAddr pa = pad_addr(work_all + grp * kWorkPad, T, w, lane);
   auto tw3 = [&]() { double2 t[4]; tm_ld4(ttw, t); return Tw4x{t[0], t[1], t[2], t[3]}; };
   auto tw4 = [&]() { double2 t[4]; tm_ld4(ttw + 16, t); return Tw4x{t[0], t[1], t[2], t[3]}; };
-  const double sgn_d = A.sign < 0 ? -1.0 : 1.0;
-  const uint32_t sgn_bit = A.sign < 0 ? 1u : 0u;
+  const double sgn_d = (MODE == MODE_TRACE && A.sign < 0) ? -1.0 : 1.0;
+  const uint32_t sgn_bit = (MODE == MODE_TRACE && A.sign < 0) ? 1u : 0u;
   unsigned long long* xc = xp + co * kN;  // the words this CTA produces
   // CTA 0's copy of the mask column, as seen from CTA 1
   const uint32_t remote_mask = map_to_cta(smem_u32(xp + kN), 0);
@@ -86,31 +88,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
   const int n_clusters = gridDim.x >> 1;
   for (int item = blockIdx.x >> 1; item < A.n_items; item += n_clusters) {
     int* dst = A.dst + (size_t)item * A.ct_stride;
+    // COMBINE2: words of S = rsh1(a X^-t + b) of this CTA's column, in its global scratch
+    unsigned long long* sw = A.scratch
+        ? reinterpret_cast<unsigned long long*>(A.scratch + (size_t)blockIdx.x * A.ct_stride) : nullptr;
     const int* src;
     {
       long idx = item;
-      if (A.src_div > 0) idx = item / A.src_div;
+      if (MODE == MODE_COMBINE2) idx = 2L * item;
+      else if (A.src_div > 0) idx = item / A.src_div;
       else if (A.src_mod > 0) { int r = item % A.src_mod; idx = A.src_map ? A.src_map[r] : r; }
       src = A.src + idx * A.ct_stride;
     }
     const size_t mat_off = A.mat_div > 0 ? (size_t)(item / A.mat_div) * A.mat_stride : 0;
 
-    // -------- prologue: x = rsh1(src * X^rk); both CTAs need the mask column, CTA 0 also the body --------
+    // -------- prologue: both CTAs need the mask column of x (TRACE) / D (COMBINE2), CTA 0 also the body --------
+    // CTA 0: group 0 converts the body column, group 1 the mask column; CTA 1: both groups half of the mask
     {
-      int rk = A.rot_const;
-      if (A.rot_mod > 0) rk += A.rot_mul * (item % A.rot_mod);
-      rk &= (2 * kN - 1);
-      // CTA 0: group 0 converts the body column, group 1 the mask column; CTA 1: both groups half of the mask
       const int col = co == 0 ? grp : 1;
       const int m0 = co == 0 ? 0 : 8 * grp, m1 = co == 0 ? 16 : 8 * grp + 8;
+      if (MODE == MODE_TRACE) {
+        // x = rsh1(src * X^rk)
+        int rk = A.rot_const;
+        if (A.rot_mod > 0) rk += A.rot_mul * (item % A.rot_mod);
+        rk &= (2 * kN - 1);
 #pragma unroll 4
-      for (int m = m0; m < m1; m++) {
-        const int i = T + 256 * m;
-        bool neg;
-        const int j = rot_index(i, 2 * kN - rk, neg);
-        long long X = limbs_value(src[CT(col, 0) + j], src[CT(col, 1) + j], src[CT(col, 2) + j]);
-        if (neg) X = -X;
-        xp[col * kN + i] = rsh1_word(X);
+        for (int m = m0; m < m1; m++) {
+          const int i = T + 256 * m;
+          bool neg;
+          const int j = rot_index(i, 2 * kN - rk, neg);
+          long long X = limbs_value(src[CT(col, 0) + j], src[CT(col, 1) + j], src[CT(col, 2) + j]);
+          if (neg) X = -X;
+          xp[col * kN + i] = rsh1_word(X);
+        }
+      } else {
+        // a1 = a X^-t;  D = rsh1(a1 - b) -> xp;  S = rsh1(a1 + b) -> sw (own column only)
+        const int* a = src;
+        const int* b = src + A.ct_stride;
+        const int tt = A.rot_const;
+#pragma unroll 1
+        for (int mc = m0; mc < m1; mc += 8) {
+          int av[8][3], bv[8][3];
+          bool ng[8];
+#pragma unroll
+          for (int mm = 0; mm < 8; mm++) {
+            const int i = T + 256 * (mc + mm);
+            const int j = rot_index(i, tt, ng[mm]);  // (a X^-t)[i] = +/- a[(i + t) mod 2N]
+#pragma unroll
+            for (int l = 0; l < 3; l++) { av[mm][l] = a[CT(col, l) + j]; bv[mm][l] = b[CT(col, l) + i]; }
+          }
+#pragma unroll
+          for (int mm = 0; mm < 8; mm++) {
+            const int i = T + 256 * (mc + mm);
+            long long Xa = limbs_value(av[mm][0], av[mm][1], av[mm][2]);
+            if (ng[mm]) Xa = -Xa;
+            const long long Xb = limbs_value(bv[mm][0], bv[mm][1], bv[mm][2]);
+            xp[col * kN + i] = rsh1_word(Xa - Xb);
+            if (col == co) sw[i] = rsh1_word(Xa + Xb);
+          }
+        }
       }
     }
     __syncthreads();
@@ -177,7 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
         if (step == 0 && rho != 1) prefetch(1);
       }
       if (co == 0 && grp == 1) {
-        // body-column accumulator init: x_body + s phi_g(x_body)
+        // body-column accumulator init: TRACE x_body + s phi_g(x_body); COMBINE2 sigma (D_body[u] - bias)
         unsigned long long v0[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -185,7 +220,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
           const int e = (e0 + (q & 7) * d1 + (q >> 3) * d2) & (2 * kN - 1);
           const unsigned long long b = xp[e & (kN - 1)] - kBias51;
           const bool ng = (((sgn >> q) & 1u) ^ sgn_bit) != 0;
-          v0[q] = (ng ? 0ull - b : b) + xp[i];
+          v0[q] = (ng ? 0ull - b : b) + (MODE == MODE_TRACE ? xp[i] : 0ull);
         }
         group_sync(1);
 #pragma unroll
@@ -196,7 +231,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // spectra and the body init visible to both groups; every gather of the old mask words done
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      cluster_arrive();  // phase A: this CTA no longer reads the old mask words
+      if (MODE == MODE_TRACE) {
+        cluster_arrive();  // phase A: this CTA no longer reads the old mask words
+      } else if (co == 1) {
+        // COMBINE2, mask column: the accumulator starts from zero (the D words were only needed by the gathers)
+#pragma unroll
+        for (int q = 0; q < 8; q++) xc[tid + 512 * q] = 0ull;
+        __syncthreads();
+      }
 
       // --------- this group's two limbs of column `co`: contraction, inverse, atomic word accumulation -------
 #pragma unroll 1
@@ -244,7 +286,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
           const double v = (q < 8) ? cur[q & 7].x : cur[q & 7].y;
           unsigned long long add;
           if (l == 3) {
-            const double t = fma(v, sgn_d, kMagic52 + 65536.0);
+            const double t = MODE == MODE_TRACE ? fma(v, sgn_d, kMagic52 + 65536.0)
+                                                : v + __hiloint2double(0x43380000, (int)(65536u - ((sgn >> q) & 1u)));
             add = (unsigned long long)(long long)(int)__funnelshift_r((uint32_t)__double2loint(t), (uint32_t)__double2hiint(t), 17);
           } else {
             const double t = fma(v, sgn_d, kMagic52);
@@ -254,33 +297,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) k_ks6(
         }
       }
       __syncthreads();   // all four limbs are in the words of this CTA's column
-      cluster_wait();    // phase A complete: CTA 0 has gathered the old mask words, CTA 1 may overwrite them
-      // ------- finish the words (mask to 51 bits, rsh for the next step); CTA 1 mirrors them into CTA 0 -------
+      if (MODE == MODE_TRACE) {
+        cluster_wait();    // phase A complete: CTA 0 has gathered the old mask words, CTA 1 may overwrite them
+        // ------- finish the words (mask to 51 bits, rsh for the next step); CTA 1 mirrors them into CTA 0 -------
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int i = tid + 512 * q;
-        const unsigned long long U = xc[i] & kMask51;
-        const unsigned long long Un = last ? U : rsh1_canon(U);
-        xc[i] = Un;
-        if (co == 1) st_cluster_u64(remote_mask + 8u * (uint32_t)i, Un);
+        for (int q = 0; q < 8; q++) {
+          const int i = tid + 512 * q;
+          const unsigned long long U = xc[i] & kMask51;
+          const unsigned long long Un = last ? U : rsh1_canon(U);
+          xc[i] = Un;
+          if (co == 1) st_cluster_u64(remote_mask + 8u * (uint32_t)i, Un);
+        }
+        cluster_arrive();  // phase B: new mask words written on both sides
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        cluster_wait();    // ... and visible before the next step's gathers
+      } else {
+        // y = phi_g(normalize(KS(D)));  out = normalize(S - y) X^t:  word = S - (R + k3) [- sigma (D_body[u] - bias)]
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int i = tid + 512 * q;
+          const unsigned long long U = (sw[i] - xc[i]) & kMask51;
+          bool rneg;
+          const int dd = rot_index(i, A.rot_const, rneg);  // a' * X^t
+#pragma unroll
+          for (int ll = 0; ll < 3; ll++) {
+            const int dg = word_digit(U, ll);
+            dst[CT(co, ll) + dd] = rneg ? -dg : dg;
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      cluster_arrive();  // phase B: new mask words written on both sides
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      cluster_wait();    // ... and visible before the next step's gathers
     }  // steps
 
-    // copy-out: every CTA its own column, all 512 threads
+    if (MODE == MODE_TRACE) {
+      // copy-out: every CTA its own column, all 512 threads
 #pragma unroll 4
-    for (int q = 0; q < 8; q++) {
-      const int i = tid + 512 * q;
-      const unsigned long long U = xc[i];
-      dst[CT(co, 0) + i] = word_digit(U, 0);
-      dst[CT(co, 1) + i] = word_digit(U, 1);
-      dst[CT(co, 2) + i] = word_digit(U, 2);
+      for (int q = 0; q < 8; q++) {
+        const int i = tid + 512 * q;
+        const unsigned long long U = xc[i];
+        dst[CT(co, 0) + i] = word_digit(U, 0);
+        dst[CT(co, 1) + i] = word_digit(U, 1);
+        dst[CT(co, 2) + i] = word_digit(U, 2);
+      }
     }
-    // the next item's prologue rewrites CTA 0's mask column, which CTA 1 may still be mirroring: one more round
+    // the next item's prologue rewrites the word buffers (CTA 0's mask column is also written by CTA 1)
     cluster_arrive();
     __syncthreads();
     cluster_wait();
