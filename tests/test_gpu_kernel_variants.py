@@ -1,7 +1,7 @@
 """Every kernel generation behind the same C ABI must give the same limbs as the oracle.
 
-The library picks a kernel per launch from the launch width (narrow: column-split k_vmp / k_ks5,
-wide: k_ext3 / k_ks4).  The small parity cases of test_gpu_parity.py only produce narrow launches, so
+The library picks a kernel per launch from the launch width (narrow: column-split k_vmp / k_ks6 / k_ks5,
+wide: k_ext3 / k_ks4; the default selection is what test_gpu_parity.py itself runs).  The small parity cases of test_gpu_parity.py only produce narrow launches, so
 each variant is forced through the whole limb-level parity set (external product, chains, trace,
 packer, read / read_prepare_write / write at four parameter sets, batched, sharded) in a
 subprocess: the selection knobs are read once per process.
@@ -30,6 +30,8 @@ VARIANTS = {
     "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0"},
     # digit-domain two-CTA kernels (k_ks2 / k_ext2) and the single-CTA k_vmp without column split
     "ks2_vmp": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_SPLIT": "0"},
+    # column-split k_vmp for every narrow operation (two CTAs per operation, one launch per chain step)
+    "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0"},
 }
 
 
