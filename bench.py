@@ -187,7 +187,9 @@ def main():
             "impl": "reference", "metric": "batched_reads_per_s", "value": v, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload},
+            "data": "synthetic",
+            "config": {"workload": workload, "max_addr": max_addr, "word_size": ws, "k_pt": k_pt, "batch": args.batch,
+                       "parallelism": "host threads", "sample_reads_per_step": n_reads},
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
