@@ -186,7 +186,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "batched_reads_per_s", "value": v, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload, "max_addr": max_addr, "word_size": ws, "k_pt": k_pt, "batch": args.batch,
                        "parallelism": "host threads", "sample_reads_per_step": n_reads},
