@@ -480,17 +480,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
               cur[j].x = fma(a.x, g0[j].x, fma(-a.y, g0[j].y, cur[j].x));
               cur[j].y = fma(a.x, g0[j].y, fma(a.y, g0[j].x, cur[j].y));
             }
-            continue;
-          }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; j++) { g0[j] = __ldg(gp + 32 * j); g1[j] = __ldg(gp + (size_t)LOUT * kM + 32 * j); }
+            for (int j = 0; j < 8; j++) { g0[j] = __ldg(gp + 32 * j); g1[j] = __ldg(gp + (size_t)LOUT * kM + 32 * j); }
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const double2 a = ap[32 * j];
-            cur[j].x = fma(a.x, g0[j].x, fma(-a.y, g0[j].y, cur[j].x));
-            cur[j].y = fma(a.x, g0[j].y, fma(a.y, g0[j].x, cur[j].y));
-            nxt[j].x = fma(a.x, g1[j].x, fma(-a.y, g1[j].y, nxt[j].x));
-            nxt[j].y = fma(a.x, g1[j].y, fma(a.y, g1[j].x, nxt[j].y));
+            for (int j = 0; j < 8; j++) {
+              const double2 a = ap[32 * j];
+              cur[j].x = fma(a.x, g0[j].x, fma(-a.y, g0[j].y, cur[j].x));
+              cur[j].y = fma(a.x, g0[j].y, fma(a.y, g0[j].x, cur[j].y));
+              nxt[j].x = fma(a.x, g1[j].x, fma(-a.y, g1[j].y, nxt[j].x));
+              nxt[j].y = fma(a.x, g1[j].y, fma(a.y, g1[j].x, nxt[j].y));
+            }
           }
         }
         PHASE_TICK(3);
