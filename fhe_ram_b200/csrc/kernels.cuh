@@ -336,7 +336,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_vmp(const VmpArgs A) {
 
     for (int step = 0; step < A.n_steps; step++) {
       const double2* G = A.mat[step] + mat_off;
-      const int g = A.gal[step];
 
       // ------------------------------ prologue ------------------------------------
       if (MODE == MODE_TRACE) {
