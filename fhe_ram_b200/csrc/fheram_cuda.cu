@@ -19,6 +19,7 @@
 #include "kernels_ks4.cuh"
 #include "kernels_ks5.cuh"
 #include "kernels_ks6.cuh"
+#include "kernels_ks7.cuh"
 
 using namespace fheram;
 
@@ -165,6 +166,7 @@ struct fheram_ctx {
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
   double2* d_tw = nullptr;  // tw6 | tw7c | tw8c | tw9 | tw10c
+  double2* d_tw16 = nullptr;  // twiddles of the 16-point transform (kernels_ks7.cuh): [16][16] | [128][7]
   Twiddles tw;
   int* d_err = nullptr;
   uint64_t launches = 0;
@@ -218,6 +220,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
+  CU(cudaFuncSetAttribute(k_ks7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
+  CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
@@ -304,6 +308,23 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   c->tw.tw8c = c->d_tw + 128;
   c->tw.tw9 = c->d_tw + 256;
   c->tw.tw10c = c->d_tw + 768;
+  {
+    std::vector<double2> t16(kTw16Len);
+    t16[0] = make_double2(0, 0);
+    for (int a = 0; a < 16; a++)
+      for (int k = 1; k < 16; k++) {
+        int sl = 0;
+        while ((2 << sl) <= k) sl++;
+        zeta(4 + sl, (a << sl) + (k - (1 << sl)), &t16[16 * a + k]);
+      }
+    for (int t = 0; t < 128; t++) {
+      double2* p = &t16[256 + 7 * t];
+      zeta(8, 2 * t, p); zeta(9, 4 * t, p + 1); zeta(9, 4 * t + 2, p + 2);
+      for (int k = 0; k < 4; k++) zeta(10, 8 * t + 2 * k, p + 3 + k);
+    }
+    CU(cudaMalloc(&c->d_tw16, sizeof(double2) * kTw16Len));
+    CU(cudaMemcpy(c->d_tw16, t16.data(), sizeof(double2) * kTw16Len, cudaMemcpyHostToDevice));
+  }
   CU(cudaMalloc(&c->d_err, sizeof(int)));
   CU(cudaMemset(c->d_err, 0, sizeof(int)));
   TRY(c->scratch.ensure((size_t)c->sm_count * 2 * c->ct_stride() * sizeof(int)));
@@ -317,7 +338,7 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
-  cudaFree(c->d_tw); cudaFree(c->d_err);
+  cudaFree(c->d_tw); cudaFree(c->d_tw16); cudaFree(c->d_err);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -596,6 +617,26 @@ static int launch_ks6(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   CU(cudaGetLastError());
   return 0;
 }
+// 16-point-per-thread trace kernel (kernels_ks7.cuh): FHERAM_KS7 = 0 off, 1 wide launches, 2 every launch
+static int ks7_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KS7"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static int launch_ks7(fheram_ctx* c, const VmpArgs& a) {
+  if (a.n_items <= 0) return 0;
+  int grid = a.n_items < 2 * c->sm_count ? a.n_items : 2 * c->sm_count;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
+  k_ks7<<<grid, 256, kKs7Smem, c->stream>>>(a, c->d_tw16);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({KC_TRACE, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
 // FHERAM_KSGEN=3 selects k_ks3 instead of the pipelined k_ks4 (kernels_ks4.cuh) where ks3_mode() applies
 static bool use_ks4() {
   static int v = -1;
@@ -643,6 +684,7 @@ static int prepare(fheram_ctx* c, const int* raw, long raw_stride, double2* out,
 struct fheram_keys {
   fheram_ctx* c;
   double2* atk = nullptr;      // [log_n] prepared trace keys
+  double2* atk7 = nullptr;     // trace keys prepared in the frequency order of k_ks7
   double2* atk_inv = nullptr;  // prepared atk_ggsw_inv
   double2* tsk = nullptr;      // prepared tsk_ggsw_inv
 };
@@ -667,6 +709,19 @@ extern "C" int fheram_keys_prepare(fheram_ctx* c, const int64_t* atk_glwe, const
     TRY(prepare(c, tmp + (size_t)i * atk_raw, (long)atk_raw, k->atk + (size_t)i * c->atk_prep_len(),
                 c->atk_prep_len(), 1, d.dnum_ct, 1, d.size_evk_trace,
                 (int)((galois(d.log_n, i) + 2 * kN) % (2 * kN))));
+  CU(cudaMalloc(&k->atk7, sizeof(double2) * c->atk_prep_len() * d.log_n));
+  for (int i = 0; i < d.log_n; i++) {
+    Prep7Args pa;
+    pa.p.raw = tmp + (size_t)i * atk_raw; pa.p.out = k->atk7 + (size_t)i * c->atk_prep_len();
+    pa.p.raw_stride = (long)atk_raw; pa.p.out_stride = c->atk_prep_len();
+    pa.p.rows = d.dnum_ct; pa.p.cin = 1; pa.p.lout = d.size_evk_trace; pa.p.tw = c->tw;
+    pa.p.gal_inv = inv_mod_2n((int)((galois(d.log_n, i) + 2 * kN) % (2 * kN)));
+    pa.tw16 = c->d_tw16;
+    pa.n_polys = d.dnum_ct * 2 * d.size_evk_trace;
+    k_prepare7<<<(pa.n_polys + 1) / 2, 256, kPrep7Smem, c->stream>>>(pa);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
   CU(cudaStreamSynchronize(c->stream));
   TRY(upload_i64(c, atk_inv, inv_raw, tmp));
   TRY(prepare(c, tmp, (long)inv_raw, k->atk_inv, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv,
@@ -682,7 +737,7 @@ extern "C" int fheram_keys_prepare(fheram_ctx* c, const int64_t* atk_glwe, const
 extern "C" int fheram_keys_destroy(fheram_keys* k) {
   if (!k) return 0;
   cudaSetDevice(k->c->device);
-  cudaFree(k->atk); cudaFree(k->atk_inv); cudaFree(k->tsk);
+  cudaFree(k->atk); cudaFree(k->atk7); cudaFree(k->atk_inv); cudaFree(k->tsk);
   delete k;
   return 0;
 }
@@ -860,6 +915,11 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     c->launches++;
     CU(cudaGetLastError());
     return 0;
+  }
+  if (ks7_mode() == 2 || (ks7_mode() == 1 && n_items > c->sm_count)) {
+    VmpArgs b = a;
+    for (int s = 0; s < b.n_steps; s++) b.mat[s] = k->atk7 + (size_t)(g0 + s) * c->atk_prep_len();
+    return launch_ks7(c, b);
   }
   if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, k_ks6<MODE_TRACE>, a, KC_TRACE);
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count)) return launch_ks5(c, k_ks5<MODE_TRACE>, a, KC_TRACE);

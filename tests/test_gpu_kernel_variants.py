@@ -23,15 +23,17 @@ SELECT = ("test_external_product_matches_oracle or test_external_product_adversa
 
 VARIANTS = {
     # word-domain key switch, in-place accumulation + double-buffered tiles (k_ks4) and padded k_ext3
-    "ks4_ext3": {"FHERAM_KS3": "2", "FHERAM_KS5": "0"},
+    "ks4_ext3": {"FHERAM_KS3": "2", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
+    # 16-point-per-thread transform with two exchanges, two polynomials per CTA (k_ks7) for every trace chain
+    "ks7": {"FHERAM_KS7": "2"},
     # word-domain key switch with register accumulators (k_ks3)
-    "ks3": {"FHERAM_KS3": "2", "FHERAM_KSGEN": "3", "FHERAM_KS5": "0"},
+    "ks3": {"FHERAM_KS3": "2", "FHERAM_KSGEN": "3", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
     # one operation per SM, 512 threads, tiles parked in tensor memory (k_ks5), trace and combine
-    "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0"},
+    "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0", "FHERAM_KS7": "0"},
     # digit-domain two-CTA kernels (k_ks2 / k_ext2) and the single-CTA k_vmp without column split
-    "ks2_vmp": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_SPLIT": "0"},
+    "ks2_vmp": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_SPLIT": "0", "FHERAM_KS7": "0"},
     # column-split k_vmp for every narrow operation (two CTAs per operation, one launch per chain step)
-    "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0"},
+    "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
 }
 
 
