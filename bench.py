@@ -436,7 +436,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": {"ext": "k_ext3", "trace": "k_ks4<TRACE>", "combine2": "k_ks4<COMBINE2>"}[dom],
+        "bound": "fp64", "kernel": {"ext": "k_ext3", "trace": "k_ks7", "combine2": "k_ks4<COMBINE2>"}[dom],
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "fp64 FMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry; "
