@@ -1334,10 +1334,14 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
   }
   Set* sets = hp.sets;
   cudaStream_t copy_stream = hp.copy_stream;
-  const int n_chunks = (n + chunk - 1) / chunk;
+  // chunk boundaries: the first chunks are small (their upload is not overlapped with anything), then full size
+  std::vector<int> start;
+  for (int b = 0, sz = chunk >= 64 ? 16 : chunk; b < n; b += sz, sz = sz * 2 < chunk ? sz * 2 : chunk) start.push_back(b);
+  start.push_back(n);
+  const int n_chunks = (int)start.size() - 1;
   auto issue_copy = [&](int ci) -> int {
     Set& s = sets[ci & 1];
-    const int b0 = ci * chunk, nb = n - b0 < chunk ? n - b0 : chunk;
+    const int b0 = start[ci], nb = start[ci + 1] - b0;
     if (ci >= 2) CU(cudaStreamWaitEvent(copy_stream, s.freed, 0));
     CU(cudaMemcpyAsync(s.stage, ggsw_host + (size_t)b0 * per_addr, sizeof(long long) * nb * per_addr,
                        cudaMemcpyHostToDevice, copy_stream));
@@ -1348,7 +1352,7 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
   for (int ci = 0; ci < n_chunks; ci++) {
     if (ci + 1 < n_chunks) TRYC(issue_copy(ci + 1));
     Set& s = sets[ci & 1];
-    const int b0 = ci * chunk, nb = n - b0 < chunk ? n - b0 : chunk;
+    const int b0 = start[ci], nb = start[ci + 1] - b0;
     s.a.count = nb;
     CUC(cudaStreamWaitEvent(c->stream, s.copied, 0));
     k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
