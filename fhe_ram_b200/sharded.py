@@ -147,48 +147,59 @@ class ShardedRam:
         G, rank = self.world, self.rank
         per = params.n_ggsw() * params.ggsw_len()          # int32 limbs per address on the device
 
-        # host-buffer path, pipelined in chunks of `chunk` reads per rank: every rank uploads only its own
-        # addresses over PCIe on a copy stream (the others arrive over NVLink with one all-gather per
-        # chunk), so the upload of chunk k+1 overlaps prepare / read / exchange / finish of chunk k
-        chunk = max(1, min(64, max(16, B // G // 4), B // G))  # at least four pipeline stages when the slice allows
-        n_chunks = (B // G + chunk - 1) // chunk
-        sets = [api.Address.device_alloc(params, chunk * G) for _ in range(2)]
-        L = params.word_size() * params.glwe_len()
+        # host-buffer path, pipelined in chunks of reads per rank: every rank uploads only its own addresses over
+        # PCIe on a copy stream (the others arrive over NVLink with one all-gather per chunk), so the upload of
+        # chunk k+1 overlaps prepare / read / exchange / finish of chunk k.  The first chunks are small (their
+        # upload overlaps nothing), then the size doubles up to `chunk`.
+        cnt = B // G
+        chunk = max(1, min(64, max(16, cnt // 4), cnt))
+        sched = []                                  # (first read of the rank's slice, reads) per chunk
+        b, sz = 0, min(8, chunk)
+        while b < cnt:
+            nb = min(sz, cnt - b)
+            sched.append((b, nb))
+            b += nb
+            sz = min(2 * sz, chunk)
+        # two address sets per chunk size (double buffering), each sized exactly: G * nb addresses
+        sets = {}
+        for _, nb in sched:
+            if nb not in sets:
+                sets[nb] = [api.Address.device_alloc(params, nb * G) for _ in range(2)]
+        use = []                                    # address set of every chunk (alternating within a size)
+        seen = {}
+        for _, nb in sched:
+            k = seen.get(nb, 0)
+            use.append(sets[nb][k & 1])
+            seen[nb] = k + 1
 
         def run_e2e():
-            cnt = B // G
-
             def issue_upload(ci):
-                a = sets[ci & 1]
-                b0 = rank * cnt + ci * chunk
-                nb = min(chunk, cnt - ci * chunk)
-                # chunk layout on the device: [G ranks][chunk] so that one all-gather completes it
-                a.upload_slice_async(addr_limbs[b0:b0 + nb], rank * chunk, nb)
+                b0, nb = sched[ci]
+                # chunk layout on the device: [G ranks][nb] so that one all-gather completes it
+                use[ci].upload_slice_async(addr_limbs[rank * cnt + b0:rank * cnt + b0 + nb], rank * nb, nb)
 
             issue_upload(0)
-            for ci in range(n_chunks):
-                if ci + 1 < n_chunks:
+            for ci, (b0, nb) in enumerate(sched):
+                if ci + 1 < len(sched):
                     issue_upload(ci + 1)
-                a = sets[ci & 1]
-                nb = min(chunk, cnt - ci * chunk)
+                a = use[ci]
                 a.wait_upload()
                 if G > 1:
-                    full = torch.as_tensor(_DevView(a.raw_ptr(), G * chunk * per), device=f"cuda:{params.device}")
-                    dist.all_gather_into_tensor(full, full[rank * chunk * per:(rank + 1) * chunk * per])
+                    full = torch.as_tensor(_DevView(a.raw_ptr(), G * nb * per), device=f"cuda:{params.device}")
+                    dist.all_gather_into_tensor(full, full[rank * nb * per:(rank + 1) * nb * per])
                 a.prepare()
-                # the chunk holds G*chunk addresses, [r][j] = read (r*cnt + ci*chunk + j): this rank finishes
-                # the `chunk` reads of its own row
-                part = self.e.read_local(a, keys)                      # [G*chunk][ws] local partials
+                # the chunk holds G*nb addresses, [r][j] = read (r*cnt + b0 + j): this rank finishes the nb reads
+                # of its own row
+                part = self.e.read_local(a, keys)                      # [G*nb][ws] local partials
                 if G > 1:
                     recv = self.e.empty(part.numel())
                     dist.all_to_all_single(recv, part)
                 else:
                     recv = part
-                mine = self.e.read_finish(recv, chunk, a, rank * chunk, keys)
+                mine = self.e.read_finish(recv, nb, a, rank * nb, keys)
                 a.release()
                 api._check(api.lib().fheram_download_glwe(params.module(), C.c_void_p(mine.data_ptr()),
-                                                          nb * params.word_size(),
-                                                          api._p(out_host[ci * chunk:ci * chunk + nb])))
+                                                          nb * params.word_size(), api._p(out_host[b0:b0 + nb])))
             return out_host
 
         return run_resident, run_e2e
