@@ -35,3 +35,23 @@ def test_committed_b200_line_has_the_contract_keys():
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["gpu_launches"] > 0 and not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_clock_sampler_window_selection():
+    """bench.ClockSampler keeps the samples of the timed window and falls back to the whole span when the window is
+    shorter than the sampling period (8-GPU runs: 0.2 s timed regions)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    row = lambda mhz, cap: [str(mhz), "1965", "700.0", "Not Active", "Not Active", "Not Active", cap]
+    s.rows = [(10.0, row(1500, "Not Active")), (11.0, row(1965, "Active")), (12.0, row(1965, "Not Active")), (13.0, row(300, "Not Active"))]
+    s.t0, s.t1 = 10.9, 12.1
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    s = bench.ClockSampler(0)
+    s.rows = [(10.0, row(1965, "Not Active")), (13.0, row(1965, "Not Active"))]
+    s.t0, s.t1 = 11.0, 11.2
+    out = s.stop()
+    assert out["samples"] == 2 and out["window"].startswith("warm-up")
