@@ -220,7 +220,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
-  CU(cudaFuncSetAttribute(k_ks7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
+  CU(cudaFuncSetAttribute(k_ks7<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
+  CU(cudaFuncSetAttribute(k_ks7<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
@@ -623,15 +624,16 @@ static int ks7_mode() {
   if (v < 0) { const char* e = getenv("FHERAM_KS7"); v = e ? atoi(e) : 1; }
   return v;
 }
-static int launch_ks7(fheram_ctx* c, const VmpArgs& a) {
+template <typename K>
+static int launch_ks7(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   if (a.n_items <= 0) return 0;
   int grid = a.n_items < 2 * c->sm_count ? a.n_items : 2 * c->sm_count;
   size_t e0 = 0;
   if (c->profile) e0 = prof_event(c);
-  k_ks7<<<grid, 256, kKs7Smem, c->stream>>>(a, c->d_tw16);
+  kernel<<<grid, 256, kKs7Smem, c->stream>>>(a, c->d_tw16);
   if (c->profile) {
     size_t e1 = prof_event(c);
-    c->ev_recs.push_back({KC_TRACE, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
   }
   c->launches++;
   CU(cudaGetLastError());
@@ -919,7 +921,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   if (ks7_mode() == 2 || (ks7_mode() == 1 && n_items > c->sm_count)) {
     VmpArgs b = a;
     for (int s = 0; s < b.n_steps; s++) b.mat[s] = k->atk7 + (size_t)(g0 + s) * c->atk_prep_len();
-    return launch_ks7(c, b);
+    return launch_ks7(c, k_ks7<MODE_TRACE>, b, KC_TRACE);
   }
   if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, k_ks6<MODE_TRACE>, a, KC_TRACE);
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count)) return launch_ks5(c, k_ks5<MODE_TRACE>, a, KC_TRACE);
@@ -959,6 +961,15 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  {
+    static int ks7c = -1;  // two-sided combine on k_ks7: FHERAM_KS7C = 0 off, 1 wide launches, 2 every launch
+    if (ks7c < 0) { const char* e = getenv("FHERAM_KS7C"); ks7c = e ? atoi(e) : 0; }
+    if (ks7c == 2 || (ks7c == 1 && n_items > c->sm_count)) {
+      VmpArgs b = a;
+      b.mat[0] = k->atk7 + (size_t)level * c->atk_prep_len();
+      return launch_ks7(c, k_ks7<MODE_COMBINE2>, b, KC_COMBINE2);
+    }
+  }
   if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, k_ks6<MODE_COMBINE2>, a, KC_COMBINE2);
   // one item per SM where two CTAs per item no longer fit (75 .. sm_count items): 37-39 us against 45 us of k_vmp
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count && 2 * n_items > c->sm_count))

@@ -26,6 +26,8 @@ VARIANTS = {
     "ks4_ext3": {"FHERAM_KS3": "2", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
     # 16-point-per-thread transform with two exchanges, two polynomials per CTA (k_ks7) for every trace chain
     "ks7": {"FHERAM_KS7": "2"},
+    # the same kernel for the packer's two-sided combine as well (k_ks7<MODE_COMBINE2>)
+    "ks7c": {"FHERAM_KS7": "2", "FHERAM_KS7C": "2"},
     # word-domain key switch with register accumulators (k_ks3)
     "ks3": {"FHERAM_KS3": "2", "FHERAM_KSGEN": "3", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
     # one operation per SM, 512 threads, tiles parked in tensor memory (k_ks5), trace and combine
