@@ -219,8 +219,10 @@ def main():
     import ctypes as C
     cts = np.zeros(ws * params.n_glwe() * params.glwe_len(), dtype=np.int64)
     xa, xe = fr.Source(11), fr.Source(12)
+    t0 = time.perf_counter()
     api._check(api.lib().fheram_encrypt_ram(C.byref(params.c), data.ctypes.data_as(api._PU8), api._p(sk.data),
                                             xa.h, xe.h, api._p(cts)))
+    t_ram_cpu = time.perf_counter() - t0
     B = args.batch
     rng = np.random.default_rng(7)
     idxs = rng.integers(0, max_addr, size=B)
@@ -391,6 +393,30 @@ def main():
             params.synchronize(); wr.append((time.perf_counter() - t0) * 1e3)
         lat["read_prepare_write_ms"] = float(np.median(rpw))
         lat["write_ms"] = float(np.median(wr))
+
+    # ---- Ram::encrypt_sk / Address::encrypt_sk on the device (k_glwe_encrypt), set-up path,
+    #      outside every timed region above; checked limb for limb against the CPU client side ----
+    if world == 1:
+        r2 = fr.Ram.new(params)
+        r2.encrypt_sk_gpu(data, sk, fr.Source(11), fr.Source(12))  # first call: allocations
+        params.synchronize(); t0 = time.perf_counter()
+        r2.encrypt_sk_gpu(data, sk, fr.Source(11), fr.Source(12))
+        params.synchronize(); t_ram_gpu = time.perf_counter() - t0
+        assert np.array_equal(r2.store(), cts), "device Ram::encrypt_sk != client side"
+        r2.close()
+        na = min(B, 256)
+        xas, xes = [fr.Source(1000 + j) for j in range(na)], [fr.Source(5000 + j) for j in range(na)]
+        t0 = time.perf_counter()
+        dev = fr.Address.encrypt_sk_gpu(params, idxs[:na], sk, xas, xes)
+        params.synchronize(); t_addr_gpu = time.perf_counter() - t0
+        assert np.array_equal(dev.download_raw().reshape(na, -1), addr_limbs[:na]), "device Address::encrypt_sk != client side"
+        dev.close()
+        lat["client_side_encrypt"] = {
+            "ram_glwe": int(ws * params.n_glwe()), "ram_cpu_s": round(t_ram_cpu, 3), "ram_gpu_s": round(t_ram_gpu, 4),
+            "addresses": na, "address_cpu_per_s": round(B / t_addr, 1), "address_cpu_threads": threads,
+            "address_gpu_per_s": round(na / t_addr_gpu, 1),
+            "note": "GPU path: mask (ChaCha20), product with the secret and normalization on the device, noise "
+                    "drawn on host threads; limbs equal to the CPU client side (asserted)"}
 
     # ---- BASELINE config 2: external-product microbenchmark (4096 GLWE x one prepared GGSW) ----
     micro = None

@@ -125,6 +125,9 @@ SIGNATURES = {
     "fheram_encrypt_address": (C.c_int, [_PP, C.c_uint32, _P64, _V, _V, _P64]),
     "fheram_encrypt_word": (C.c_int, [_PP, C.c_uint8, _P64, _V, _V, _P64]),
     "fheram_decrypt_word": (C.c_int, [_PP, _P64, _P64, C.c_int64, _P64, C.POINTER(C.c_double)]),
+    "fheram_ram_encrypt_sk": (C.c_int, [_V, _PU8, _P64, _V, _V]),
+    "fheram_address_encrypt_sk": (C.c_int, [_V, C.c_int, C.c_int, C.POINTER(C.c_uint32), _P64,
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]),
 }
 
 _lib = None
@@ -405,6 +408,33 @@ class Address:
         a.h = h
         return a
 
+    @classmethod
+    def encrypt_sk_gpu(cls, params: Parameters, values, sk: GLWESecret, sources_xa, sources_xe,
+                       prepare: bool = True) -> "Address":
+        """src/address.rs:86-109 for every value, on the device (k_glwe_encrypt): the same limbs as
+        `encrypt_sk` from the same Sources.  One (xa, xe) pair for all addresses in turn, or one pair
+        per address.  Returns the device-resident address set, prepared."""
+        values = np.ascontiguousarray(values, dtype=np.uint32).reshape(-1)
+        xas = list(sources_xa) if isinstance(sources_xa, (list, tuple)) else [sources_xa]
+        xes = list(sources_xe) if isinstance(sources_xe, (list, tuple)) else [sources_xe]
+        if len(xas) != len(xes) or len(xas) not in (1, values.size):
+            raise FheRamError(-1, "one Source pair, or one pair per address")
+        a = cls.device_alloc(params, int(values.size))
+        ha = (C.c_void_p * len(xas))(*[x.h for x in xas])
+        he = (C.c_void_p * len(xes))(*[x.h for x in xes])
+        _check(lib().fheram_address_encrypt_sk(a.h, 0, int(values.size), values.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                               _p(sk.data), ha, he, len(xas)))
+        return a.prepare() if prepare else a
+
+    def download_raw(self) -> np.ndarray:
+        """raw GGSW limbs of a device address set as int64 (tests)"""
+        per = self.params.n_ggsw() * self.params.ggsw_len()
+        out = np.zeros(self.count * per, dtype=np.int64)
+        n_glwe_units = out.size // self.params.glwe_len()
+        assert n_glwe_units * self.params.glwe_len() == out.size
+        _check(lib().fheram_download_glwe(self.params.module(), C.c_void_p(self.raw_ptr()), n_glwe_units, _p(out)))
+        return out
+
     def upload_slice(self, limbs: np.ndarray, first: int, count: int):
         _check(lib().fheram_address_upload_slice(self.h, _p(np.ascontiguousarray(limbs, dtype=np.int64).reshape(-1)),
                                                  first, count))
@@ -486,6 +516,18 @@ class Ram:
                                         source_xa.h, source_xe.h, _p(cts)))
         self.load(cts)
         return cts
+
+    def encrypt_sk_gpu(self, data, sk: GLWESecret, source_xa: Source, source_xe: Source) -> None:
+        """src/ram.rs:129-167 on the device (k_glwe_encrypt), straight into the resident RAM: the same
+        limbs as `encrypt_sk` from the same Sources, without the host round trip."""
+        p = self.params
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ws = p.word_size()
+        if data.size % ws != 0:
+            raise FheRamError(-1, f"invalid data: data.len()%ram_chunks={data.size % ws} != 0")
+        if data.size // ws != p.max_addr():
+            raise FheRamError(-1, f"invalid data: data.len()/ram_chunks={data.size // ws} != max_addr={p.max_addr()}")
+        _check(lib().fheram_ram_encrypt_sk(self.h, data.ctypes.data_as(_PU8), _p(sk.data), source_xa.h, source_xe.h))
 
     def load(self, cts: np.ndarray):
         _check(lib().fheram_ram_load(self.h, _p(np.ascontiguousarray(cts, dtype=np.int64))))

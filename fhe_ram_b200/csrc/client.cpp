@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/fheram.h"
+#include "client_internal.h"
 
 void fheram_set_error(const char* msg);  // fheram_cuda.cu
 
@@ -87,6 +88,21 @@ extern "C" void fheram_source_fill_bytes(fheram_source* s, uint8_t* out, size_t 
     uint32_t w = s->u32();
     for (int b = 0; b < 4 && i < n; b++, i++) out[i] = (uint8_t)(w >> (8 * b));
   }
+}
+
+// ---- stream position helpers of the GPU bulk-encryption path (client_internal.h) ----
+void fheram_source_tell(const fheram_source* s, uint32_t key[8], uint64_t* word_pos) {
+  for (int i = 0; i < 8; i++) key[i] = s->key[i];
+  *word_pos = s->counter * 16 + (u64)s->pos - 16;  // counter blocks produced, 16 - pos words of the last unread
+}
+void fheram_source_skip_words(fheram_source* s, uint64_t n) {
+  const u64 wp = s->counter * 16 + (u64)s->pos - 16 + n;
+  s->counter = wp / 16;
+  s->pos = 16;
+  if (wp % 16) { s->refill(); s->pos = (int)(wp % 16); }
+}
+void fheram_source_noise_i8(fheram_source* s, int8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = (int8_t)s->gauss(3.2, 19.2);
 }
 
 namespace {
@@ -345,19 +361,13 @@ extern "C" int fheram_encrypt_ram(const fheram_params* p, const uint8_t* data, c
   return 0;
 }
 
-extern "C" int fheram_encrypt_address(const fheram_params* p, uint32_t value, const int64_t* sk,
-                                      fheram_source* xa, fheram_source* xe, int64_t* ggsw) {
-  if (check(p) || !sk || !xa || !xe || !ggsw) return FHERAM_ERR_INVALID;
+int fheram_address_monomials(const fheram_params* p, uint32_t value, int32_t* pos_out, int32_t* sign_out) {
+  if (check(p)) return FHERAM_ERR_INVALID;
   const Dims d = dims(p);
   if ((u64)value >= p->max_addr) {
     fheram_set_error("address out of range (src/address.rs:96)");
     return FHERAM_ERR_INVALID;
   }
-  Ring R(d.log_n);
-  std::vector<cd> s_spec;
-  R.forward(sk, s_spec);
-  const size_t ggsw_len = fheram_ggsw_len(p);
-  std::vector<i64> scalar(d.n, 0);
   u64 remain2d = value;
   int g = 0;
   for (int ci = 0; ci < d.n_coord; ci++) {  // src/address.rs:102-108
@@ -370,16 +380,33 @@ extern "C" int fheram_encrypt_address(const fheram_params* p, uint32_t value, co
     for (int k = 0; k < d.coord_len[ci]; k++) {  // src/coordinate.rs:148-179
       const int base = d.coord_digits[ci][k];
       const u64 chunk = (remain & ((1ull << base) - 1)) << tot_base;
-      size_t pos;
-      if (sign < 0 && chunk != 0) { pos = d.n - chunk; scalar[pos] = -1; }
-      else { pos = chunk; scalar[pos] = 1; }
-      ggsw_encrypt(R, d, p->k_addr, ggsw + (size_t)g * ggsw_len, scalar.data(), s_spec, xa, xe);
-      scalar[pos] = 0;
+      if (sign < 0 && chunk != 0) { pos_out[g] = (int32_t)(d.n - chunk); sign_out[g] = -1; }
+      else { pos_out[g] = (int32_t)chunk; sign_out[g] = 1; }
       remain >>= base;
       tot_base += base;
       g++;
     }
     remain2d /= max;
+  }
+  return g;
+}
+
+extern "C" int fheram_encrypt_address(const fheram_params* p, uint32_t value, const int64_t* sk,
+                                      fheram_source* xa, fheram_source* xe, int64_t* ggsw) {
+  if (check(p) || !sk || !xa || !xe || !ggsw) return FHERAM_ERR_INVALID;
+  const Dims d = dims(p);
+  int32_t pos[64], sign[64];
+  const int n_ggsw = fheram_address_monomials(p, value, pos, sign);
+  if (n_ggsw < 0) return n_ggsw;
+  Ring R(d.log_n);
+  std::vector<cd> s_spec;
+  R.forward(sk, s_spec);
+  const size_t ggsw_len = fheram_ggsw_len(p);
+  std::vector<i64> scalar(d.n, 0);
+  for (int g = 0; g < n_ggsw; g++) {
+    scalar[pos[g]] = sign[g];
+    ggsw_encrypt(R, d, p->k_addr, ggsw + (size_t)g * ggsw_len, scalar.data(), s_spec, xa, xe);
+    scalar[pos[g]] = 0;
   }
   return 0;
 }

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fheram.h"
@@ -20,6 +21,8 @@
 #include "kernels_ks5.cuh"
 #include "kernels_ks6.cuh"
 #include "kernels_ks7.cuh"
+#include "kernels_enc.cuh"
+#include "client_internal.h"
 
 using namespace fheram;
 
@@ -1116,6 +1119,172 @@ extern "C" int fheram_ram_tree_store(fheram_ram* r, int64_t* cts) {
   return download_i64(r->c, r->tree, (size_t)r->c->params.word_size * r->c->ct_stride(), cts);
 }
 extern "C" int fheram_ram_state(const fheram_ram* r) { return r && r->state ? 1 : 0; }
+
+// --------------------------------------------------------------------------------------
+// Bulk secret-key encryption on the device: k_glwe_encrypt regenerates the
+// mask from the Source's ChaCha20 stream, multiplies by the secret and normalizes; the noise
+// is drawn on the host in the order client.cpp draws it.  Limb-for-limb equal to
+// fheram_encrypt_ram / fheram_encrypt_address on the same Sources (tests/test_gpu_encrypt.py).
+// --------------------------------------------------------------------------------------
+struct EncBatch {
+  int n_glwe = 0, size = 0, k_noise = 0;
+  std::vector<int8_t> noise;             // [n_glwe][N]
+  std::vector<int8_t> pt;                // [n_glwe][N] or empty
+  int pt_l = 0, pt_sh = 0;
+  std::vector<int> mono;                 // [n_glwe] or empty
+  std::vector<int> seq;                  // [n_glwe] position of each GLWE in its stream, or empty (= j % glwe_per_stream)
+  std::vector<uint32_t> keys;            // [n_streams][8]
+  std::vector<unsigned long long> word0; // [n_streams]
+  int glwe_per_stream = 1;
+};
+static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, int* d_out, long stride) {
+  const int n = c->d.n;
+  DevBuf skraw, skspec, noise, pt, mono, seq, keys, word0;
+  auto cleanup = [&]() {
+    skraw.release(); skspec.release(); noise.release(); pt.release(); mono.release(); seq.release();
+    keys.release(); word0.release();
+  };
+  int rc = 0;
+#define ENC_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+#define ENC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  {
+    std::vector<int> s32((size_t)2 * n, 0);
+    for (int i = 0; i < n; i++) {
+      if (sk[i] < -1 || sk[i] > 1) return fail(FHERAM_ERR_INVALID, "secret key is not ternary");
+      s32[i] = (int)sk[i];
+    }
+    ENC_TRY(skraw.ensure(sizeof(int) * 2 * n));
+    ENC_TRY(skspec.ensure(sizeof(double2) * 2 * kM));
+    ENC_CU(cudaMemcpyAsync(skraw.p, s32.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    ENC_CU(cudaStreamSynchronize(c->stream));
+    ENC_TRY(prepare(c, (const int*)skraw.p, 2 * n, (double2*)skspec.p, 2 * kM, 1, 1, 1, 1));
+  }
+  auto up = [&](DevBuf& d, const void* h, size_t bytes) -> int {
+    if (!bytes) return 0;
+    TRY(d.ensure(bytes));
+    CU(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+  };
+  ENC_TRY(up(noise, b.noise.data(), b.noise.size()));
+  ENC_TRY(up(pt, b.pt.data(), b.pt.size()));
+  ENC_TRY(up(mono, b.mono.data(), b.mono.size() * sizeof(int)));
+  ENC_TRY(up(seq, b.seq.data(), b.seq.size() * sizeof(int)));
+  ENC_TRY(up(keys, b.keys.data(), b.keys.size() * sizeof(uint32_t)));
+  ENC_TRY(up(word0, b.word0.data(), b.word0.size() * sizeof(unsigned long long)));
+  EncArgs a;
+  a.out = d_out; a.ct_stride = stride; a.n_glwe = b.n_glwe; a.size = b.size;
+  a.nl = (b.k_noise + kK - 1) / kK - 1; a.sh = (a.nl + 1) * kK - b.k_noise;
+  a.sk_spec = (const double2*)skspec.p;
+  a.noise = (const signed char*)noise.p;
+  a.pt = b.pt.empty() ? nullptr : (const signed char*)pt.p;
+  a.pt_l = b.pt_l; a.pt_sh = b.pt_sh;
+  a.mono = b.mono.empty() ? nullptr : (const int*)mono.p;
+  a.seq = b.seq.empty() ? nullptr : (const int*)seq.p;
+  a.keys = (const uint32_t*)keys.p;
+  a.word0 = (const unsigned long long*)word0.p;
+  a.glwe_per_stream = b.glwe_per_stream;
+  a.tw = c->tw;
+  const int grid = b.n_glwe < 2 * c->sm_count ? b.n_glwe : 2 * c->sm_count;
+  k_glwe_encrypt<<<grid, kThreads, 0, c->stream>>>(a);
+  c->launches++;
+  ENC_CU(cudaGetLastError());
+  ENC_CU(cudaStreamSynchronize(c->stream));
+#undef ENC_TRY
+#undef ENC_CU
+  cleanup();
+  return 0;
+}
+
+// Ram::encrypt_sk (src/ram.rs:129-167; SubRam::encrypt_sk :334-380) into the device-resident RAM
+extern "C" int fheram_ram_encrypt_sk(fheram_ram* r, const uint8_t* data, const int64_t* sk,
+                                     fheram_source* xa, fheram_source* xe) {
+  if (!r || !data || !sk || !xa || !xe) return fail(FHERAM_ERR_INVALID, "null argument");
+  fheram_ctx* c = r->c;
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  const fheram_params& p = c->params;
+  const int ws = p.word_size, G = d.n_glwe, n = d.n;
+  const size_t total = (size_t)ws * G;
+  EncBatch b;
+  b.n_glwe = ws * r->n_local; b.size = d.size_ct; b.k_noise = p.k_ct;
+  b.pt_l = (p.k_pt + kK - 1) / kK - 1; b.pt_sh = (b.pt_l + 1) * kK - p.k_pt;
+  if (b.pt_l >= b.size) return fail(FHERAM_ERR_INVALID, "k_pt exceeds k_ct");
+  b.keys.resize(8); b.word0.resize(1);
+  fheram_source_tell(xa, b.keys.data(), (uint64_t*)&b.word0[0]);
+  b.glwe_per_stream = (int)total;
+  // noise in the order of src/ram.rs:161-166 (sub-RAM major), every polynomial of every shard
+  std::vector<int8_t> all_noise(total * n);
+  fheram_source_noise_i8(xe, all_noise.data(), all_noise.size());
+  b.noise.resize((size_t)b.n_glwe * n); b.pt.resize((size_t)b.n_glwe * n); b.seq.resize(b.n_glwe);
+  for (int s = 0; s < ws; s++)
+    for (int hp = 0; hp < r->n_local; hp++) {
+      const int h = r->shard + r->n_shards * hp;
+      const size_t jl = (size_t)s * r->n_local + hp, jg = (size_t)s * G + h;
+      b.seq[jl] = (int)jg;
+      memcpy(&b.noise[jl * n], &all_noise[jg * n], n);
+      for (int j = 0; j < n; j++) {
+        const uint64_t addr = (uint64_t)h * n + j;
+        b.pt[jl * n + j] = addr < p.max_addr ? (int8_t)data[addr * ws + s] : 0;  // src/ram.rs:364
+      }
+    }
+  TRY(run_encrypt(c, sk, b, r->data, c->ct_stride()));
+  fheram_source_skip_words(xa, 2ull * d.size_ct * n * total);
+  r->loaded = true;
+  r->state = false;
+  return 0;
+}
+
+// Address::encrypt_sk (src/address.rs:86-109) for addresses [first, first + count) of a device address set.
+// n_sources = 1: all addresses draw from (xa[0], xe[0]) one after the other, as `count` calls of
+// fheram_encrypt_address would; n_sources = count: address i draws from (xa[i], xe[i]) and the noise is
+// sampled on host threads.  Raw GGSWs only: fheram_address_prepare makes them usable.
+extern "C" int fheram_address_encrypt_sk(fheram_address* a, int first, int count, const uint32_t* values,
+                                         const int64_t* sk, fheram_source* const* xa, fheram_source* const* xe,
+                                         int n_sources) {
+  if (!a || !values || !sk || !xa || !xe || first < 0 || count < 1 || first + count > a->count ||
+      (n_sources != 1 && n_sources != count))
+    return fail(FHERAM_ERR_INVALID, "bad argument");
+  fheram_ctx* c = a->c;
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  const int n = d.n, per = d.n_ggsw * d.dnum_ct * 2;
+  EncBatch b;
+  b.n_glwe = count * per; b.size = d.size_addr; b.k_noise = c->params.k_addr;
+  b.mono.resize(b.n_glwe);
+  for (int i = 0; i < count; i++) {  // every value is checked before a Source is touched
+    int32_t pos[64], sign[64];
+    const int ng = fheram_address_monomials(&c->params, values[i], pos, sign);
+    if (ng < 0) return ng;
+    for (int g = 0; g < d.n_ggsw; g++)
+      for (int row = 0; row < d.dnum_ct; row++)
+        for (int ci = 0; ci < 2; ci++)
+          b.mono[(size_t)i * per + (g * d.dnum_ct + row) * 2 + ci] =
+              pos[g] | ((sign[g] < 0 ? 1 : 0) << 12) | (row << 16) | (ci << 24);
+  }
+  b.keys.resize((size_t)8 * n_sources); b.word0.resize(n_sources);
+  for (int i = 0; i < n_sources; i++) fheram_source_tell(xa[i], &b.keys[8 * i], (uint64_t*)&b.word0[i]);
+  b.glwe_per_stream = n_sources == 1 ? b.n_glwe : per;
+  b.noise.resize((size_t)b.n_glwe * n);
+  if (n_sources == 1) {
+    fheram_source_noise_i8(xe[0], b.noise.data(), b.noise.size());
+  } else {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
+    if ((int)nt > count) nt = count;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+      th.emplace_back([&, t]() {
+        for (int i = t; i < count; i += nt) fheram_source_noise_i8(xe[i], &b.noise[(size_t)i * per * n], (size_t)per * n);
+      });
+    for (auto& t : th) t.join();
+  }
+  const long stride = (long)2 * d.size_addr * n;
+  TRY(run_encrypt(c, sk, b, a->raw + (size_t)first * d.n_ggsw * c->ggsw_raw_len(), stride));
+  for (int i = 0; i < n_sources; i++)
+    fheram_source_skip_words(xa[i], 2ull * d.size_addr * n * (n_sources == 1 ? (uint64_t)b.n_glwe : (uint64_t)per));
+  a->inv_ready = false;
+  return 0;
+}
 
 static int first_coord_ggsw(const Derived& d, int coord) {
   int f = 0;

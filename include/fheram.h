@@ -245,6 +245,22 @@ int fheram_encrypt_word(const fheram_params *p, uint8_t value, const int64_t *sk
 int fheram_decrypt_word(const fheram_params *p, const int64_t *glwe, const int64_t *sk,
                         int64_t want, int64_t *value, double *noise);
 
+/* ---- bulk encryption on the device.  For colocated client / server set-ups (tests,
+ * benchmarks, loaders that hold the secret): the mask comes from the Source's ChaCha20 stream regenerated on
+ * the GPU, the product with the secret and the normalization run on the GPU, the noise is drawn on the host.
+ * Limb for limb what fheram_encrypt_ram / fheram_encrypt_address produce from the same Sources, and both
+ * Sources are left where those calls would leave them. ---- */
+/* Ram::encrypt_sk (src/ram.rs:129-167, SubRam::encrypt_sk :334-380) straight into the device RAM (a
+ * sharded RAM encrypts its own polynomials); data = max_addr*word_size bytes */
+int fheram_ram_encrypt_sk(fheram_ram *r, const uint8_t *data, const int64_t *sk, fheram_source *xa,
+                          fheram_source *xe);
+/* Address::encrypt_sk (src/address.rs:86-109, Coordinate::encrypt_sk src/coordinate.rs:121-180) for
+ * addresses [first, first + count) of a set from fheram_address_alloc; follow with fheram_address_prepare.
+ * n_sources = 1: every address draws from (xa[0], xe[0]) in turn; n_sources = count: one pair per address */
+int fheram_address_encrypt_sk(fheram_address *a, int first, int count, const uint32_t *values,
+                              const int64_t *sk, fheram_source *const *xa, fheram_source *const *xe,
+                              int n_sources);
+
 #ifdef __cplusplus
 }
 #endif
