@@ -415,8 +415,10 @@ def main():
             "ram_glwe": int(ws * params.n_glwe()), "ram_cpu_s": round(t_ram_cpu, 3), "ram_gpu_s": round(t_ram_gpu, 4),
             "addresses": na, "address_cpu_per_s": round(B / t_addr, 1), "address_cpu_threads": threads,
             "address_gpu_per_s": round(na / t_addr_gpu, 1),
-            "note": "GPU path: mask (ChaCha20), product with the secret and normalization on the device, noise "
-                    "drawn on host threads; limbs equal to the CPU client side (asserted)"}
+            "noise": params.encrypt_stats(),
+            "note": "GPU path: mask (ChaCha20), noise (Box-Muller on the same stream; the host re-draws the samples "
+                    "whose rounding could depend on libm's last bit), product with the secret and normalization on "
+                    "the device; limbs equal to the CPU client side (asserted)"}
 
     # ---- BASELINE config 2: external-product microbenchmark (4096 GLWE x one prepared GGSW) ----
     micro = None

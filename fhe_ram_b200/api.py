@@ -126,6 +126,7 @@ SIGNATURES = {
     "fheram_encrypt_word": (C.c_int, [_PP, C.c_uint8, _P64, _V, _V, _P64]),
     "fheram_decrypt_word": (C.c_int, [_PP, _P64, _P64, C.c_int64, _P64, C.POINTER(C.c_double)]),
     "fheram_ram_encrypt_sk": (C.c_int, [_V, _PU8, _P64, _V, _V]),
+    "fheram_debug_encrypt_stats": (C.c_int, [_V, C.POINTER(C.c_uint64)]),
     "fheram_address_encrypt_sk": (C.c_int, [_V, C.c_int, C.c_int, C.POINTER(C.c_uint32), _P64,
                                             C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]),
 }
@@ -238,6 +239,13 @@ class Parameters:
 
     def stream(self) -> int:
         return int(lib().fheram_ctx_stream(self.module()) or 0)
+
+    def encrypt_stats(self) -> dict:
+        """noise draws of the device encryption path so far: sampled on the device / re-drawn by the host /
+        streams sampled by the host"""
+        out = (C.c_uint64 * 3)()
+        _check(lib().fheram_debug_encrypt_stats(self.module(), out))
+        return {"device_draws": int(out[0]), "host_redraws": int(out[1]), "host_streams": int(out[2])}
 
     def profile(self, enable: bool):
         _check(lib().fheram_ctx_profile(self.module(), 1 if enable else 0))

@@ -101,6 +101,11 @@ void fheram_source_skip_words(fheram_source* s, uint64_t n) {
   s->pos = 16;
   if (wp % 16) { s->refill(); s->pos = (int)(wp % 16); }
 }
+int8_t fheram_source_noise_at(const fheram_source* s, uint64_t word_offset) {
+  fheram_source t = *s;
+  fheram_source_skip_words(&t, word_offset);
+  return (int8_t)t.gauss(3.2, 19.2);
+}
 void fheram_source_noise_i8(fheram_source* s, int8_t* out, size_t n) {
   for (size_t i = 0; i < n; i++) out[i] = (int8_t)s->gauss(3.2, 19.2);
 }

@@ -12,6 +12,8 @@ void fheram_source_tell(const fheram_source* s, uint32_t key[8], uint64_t* word_
 void fheram_source_skip_words(fheram_source* s, uint64_t n);
 // n draws of the GLWE encryption noise (sigma 3.2, bound 6 sigma), exactly as glwe_encrypt draws them
 void fheram_source_noise_i8(fheram_source* s, int8_t* out, size_t n);
+// the noise draw that starts `word_offset` words past the Source's position (the Source is not advanced)
+int8_t fheram_source_noise_at(const fheram_source* s, uint64_t word_offset);
 // the n_ggsw monomials +/- X^pos an address value is encoded as (src/address.rs:102-108,
 // src/coordinate.rs:148-179); returns n_ggsw or a negative status
 int fheram_address_monomials(const fheram_params* p, uint32_t value, int32_t* pos, int32_t* sign);

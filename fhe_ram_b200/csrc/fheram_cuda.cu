@@ -175,6 +175,7 @@ struct fheram_ctx {
   uint64_t launches = 0;
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
+  uint64_t enc_stats[3] = {0, 0, 0};  // noise draws sampled on the device / patched by the host / streams resampled on the host
   DevBuf opbuf[3];  // op-level entry points
   DevBuf split_tmp[2];  // ping-pong ciphertexts of the column-split (latency) schedules
   long long* d_phase = nullptr;  // per-CTA phase cycle counters (fheram_debug_phase_cycles)
@@ -1128,7 +1129,6 @@ extern "C" int fheram_ram_state(const fheram_ram* r) { return r && r->state ? 1 
 // --------------------------------------------------------------------------------------
 struct EncBatch {
   int n_glwe = 0, size = 0, k_noise = 0;
-  std::vector<int8_t> noise;             // [n_glwe][N]
   std::vector<int8_t> pt;                // [n_glwe][N] or empty
   int pt_l = 0, pt_sh = 0;
   std::vector<int> mono;                 // [n_glwe] or empty
@@ -1137,11 +1137,117 @@ struct EncBatch {
   std::vector<unsigned long long> word0; // [n_streams]
   int glwe_per_stream = 1;
 };
-static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, int* d_out, long stride) {
+// FHERAM_ENC_NOISE=host draws the noise with the host sampler only; default: k_noise_sample + host patches
+static bool enc_noise_on_device() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_ENC_NOISE"); v = (e && !strcmp(e, "host")) ? 0 : 1; }
+  return v == 1;
+}
+// widths of the report bands of k_noise_sample (tests widen them to exercise the host paths)
+static double enc_guard() {
+  static double g = -1.0;
+  if (g < 0) { const char* e = getenv("FHERAM_ENC_GUARD"); g = e ? atof(e) : 1e-9; if (!(g >= 1e-12)) g = 1e-12; }
+  return g;
+}
+static double enc_bound_guard() {
+  static double g = -1.0;
+  if (g < 0) { const char* e = getenv("FHERAM_ENC_BOUND_GUARD"); g = e ? atof(e) : enc_guard(); if (!(g >= 1e-12)) g = 1e-12; }
+  return g;
+}
+// Noise of n_streams Sources (per_stream draws each, stream-major) into d_noise, and every Source advanced as
+// that many fheram_source::gauss draws advance it.
+static int sample_noise(fheram_ctx* c, fheram_source* const* xe, int n_streams, size_t per_stream, DevBuf& d_noise) {
+  TRY(d_noise.ensure((size_t)n_streams * per_stream));
+  std::vector<int8_t> host;
+  auto host_stream = [&](int s) -> int {
+    host.resize(per_stream);
+    fheram_source_noise_i8(xe[s], host.data(), per_stream);
+    CU(cudaMemcpy((char*)d_noise.p + (size_t)s * per_stream, host.data(), per_stream, cudaMemcpyHostToDevice));
+    c->enc_stats[2]++;
+    return 0;
+  };
+  if (!enc_noise_on_device() || per_stream % 4) {  // host sampler only, one thread per stream in flight
+    std::vector<int8_t> all((size_t)n_streams * per_stream);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
+    if ((int)nt > n_streams) nt = n_streams;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+      th.emplace_back([&, t]() {
+        for (int s = t; s < n_streams; s += nt) fheram_source_noise_i8(xe[s], &all[(size_t)s * per_stream], per_stream);
+      });
+    for (auto& t : th) t.join();
+    CU(cudaMemcpy(d_noise.p, all.data(), all.size(), cudaMemcpyHostToDevice));
+    c->enc_stats[2] += n_streams;
+    return 0;
+  }
+  const unsigned max_flags = 1u << 16;
+  std::vector<uint32_t> keys((size_t)8 * n_streams);
+  std::vector<unsigned long long> w0(n_streams);
+  for (int s = 0; s < n_streams; s++) fheram_source_tell(xe[s], &keys[8 * s], (uint64_t*)&w0[s]);
+  DevBuf dk, dw, df, dn;
+  auto cleanup = [&]() { dk.release(); dw.release(); df.release(); dn.release(); };
+  int rc = 0;
+#define NZ_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+#define NZ_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  NZ_TRY(dk.ensure(keys.size() * sizeof(uint32_t)));
+  NZ_TRY(dw.ensure(w0.size() * sizeof(unsigned long long)));
+  NZ_TRY(df.ensure((size_t)max_flags * sizeof(unsigned long long)));
+  NZ_TRY(dn.ensure(sizeof(unsigned)));
+  NZ_CU(cudaMemcpyAsync(dk.p, keys.data(), keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  NZ_CU(cudaMemcpyAsync(dw.p, w0.data(), w0.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  NZ_CU(cudaMemsetAsync(dn.p, 0, sizeof(unsigned), c->stream));
+  NoiseArgs a;
+  a.out = (signed char*)d_noise.p; a.n_streams = n_streams; a.per_stream = (long)per_stream;
+  a.keys = (const uint32_t*)dk.p; a.word0 = (const unsigned long long*)dw.p; a.guard = enc_guard(); a.bound_guard = enc_bound_guard();
+  a.n_flags = (unsigned*)dn.p; a.flags = (unsigned long long*)df.p; a.max_flags = max_flags;
+  k_noise_sample<<<c->sm_count * 8, 256, 0, c->stream>>>(a);
+  c->launches++;
+  NZ_CU(cudaGetLastError());
+  unsigned n_flags = 0;
+  NZ_CU(cudaMemcpyAsync(&n_flags, dn.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NZ_CU(cudaStreamSynchronize(c->stream));
+  std::vector<char> redo(n_streams, n_flags > max_flags ? 1 : 0);  // more reports than slots: host sampling for all
+  if (n_flags && n_flags <= max_flags) {
+    std::vector<unsigned long long> flags(n_flags);
+    NZ_CU(cudaMemcpy(flags.data(), df.p, (size_t)n_flags * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (unsigned long long f : flags)
+      if ((f >> 39) & 1) redo[(size_t)(f >> 40)] = 1;
+    for (unsigned long long f : flags) {
+      const size_t s = (size_t)(f >> 40);
+      if (((f >> 39) & 1) || redo[s]) continue;
+      const unsigned long long k = f & ((1ull << 39) - 1);
+      const int8_t v = fheram_source_noise_at(xe[s], 4ull * k);
+      NZ_CU(cudaMemcpy((char*)d_noise.p + s * per_stream + k, &v, 1, cudaMemcpyHostToDevice));
+      c->enc_stats[1]++;
+    }
+  }
+  for (int s = 0; s < n_streams; s++) {
+    if (redo[s]) NZ_TRY(host_stream(s));
+    else { fheram_source_skip_words(xe[s], 4ull * per_stream); c->enc_stats[0] += per_stream; }
+  }
+#undef NZ_TRY
+#undef NZ_CU
+  cleanup();
+  return 0;
+}
+extern "C" int fheram_debug_encrypt_stats(fheram_ctx* c, uint64_t out[3]) {
+  if (!c || !out) return fail(FHERAM_ERR_INVALID, "null argument");
+  for (int i = 0; i < 3; i++) out[i] = c->enc_stats[i];
+  return 0;
+}
+
+static int check_secret(const int64_t* sk, int n) {  // before any Source moves
+  for (int i = 0; i < n; i++)
+    if (sk[i] < -1 || sk[i] > 1) return fail(FHERAM_ERR_INVALID, "secret key is not ternary");
+  return 0;
+}
+static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, const DevBuf& d_noise, bool noise_by_seq,
+                       int* d_out, long stride) {
   const int n = c->d.n;
-  DevBuf skraw, skspec, noise, pt, mono, seq, keys, word0;
+  DevBuf skraw, skspec, pt, mono, seq, keys, word0;
   auto cleanup = [&]() {
-    skraw.release(); skspec.release(); noise.release(); pt.release(); mono.release(); seq.release();
+    skraw.release(); skspec.release(); pt.release(); mono.release(); seq.release();
     keys.release(); word0.release();
   };
   int rc = 0;
@@ -1149,10 +1255,7 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, int*
 #define ENC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   {
     std::vector<int> s32((size_t)2 * n, 0);
-    for (int i = 0; i < n; i++) {
-      if (sk[i] < -1 || sk[i] > 1) return fail(FHERAM_ERR_INVALID, "secret key is not ternary");
-      s32[i] = (int)sk[i];
-    }
+    for (int i = 0; i < n; i++) s32[i] = (int)sk[i];
     ENC_TRY(skraw.ensure(sizeof(int) * 2 * n));
     ENC_TRY(skspec.ensure(sizeof(double2) * 2 * kM));
     ENC_CU(cudaMemcpyAsync(skraw.p, s32.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
@@ -1165,7 +1268,6 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, int*
     CU(cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
     return 0;
   };
-  ENC_TRY(up(noise, b.noise.data(), b.noise.size()));
   ENC_TRY(up(pt, b.pt.data(), b.pt.size()));
   ENC_TRY(up(mono, b.mono.data(), b.mono.size() * sizeof(int)));
   ENC_TRY(up(seq, b.seq.data(), b.seq.size() * sizeof(int)));
@@ -1175,7 +1277,7 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, int*
   a.out = d_out; a.ct_stride = stride; a.n_glwe = b.n_glwe; a.size = b.size;
   a.nl = (b.k_noise + kK - 1) / kK - 1; a.sh = (a.nl + 1) * kK - b.k_noise;
   a.sk_spec = (const double2*)skspec.p;
-  a.noise = (const signed char*)noise.p;
+  a.noise = (const signed char*)d_noise.p; a.noise_by_seq = noise_by_seq ? 1 : 0;
   a.pt = b.pt.empty() ? nullptr : (const signed char*)pt.p;
   a.pt_l = b.pt_l; a.pt_sh = b.pt_sh;
   a.mono = b.mono.empty() ? nullptr : (const int*)mono.p;
@@ -1199,10 +1301,12 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, int*
 extern "C" int fheram_ram_encrypt_sk(fheram_ram* r, const uint8_t* data, const int64_t* sk,
                                      fheram_source* xa, fheram_source* xe) {
   if (!r || !data || !sk || !xa || !xe) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (xa == xe) return fail(FHERAM_ERR_INVALID, "mask and noise need distinct Sources");
   fheram_ctx* c = r->c;
   CU(cudaSetDevice(c->device));
   const Derived& d = c->d;
   const fheram_params& p = c->params;
+  TRY(check_secret(sk, d.n));
   const int ws = p.word_size, G = d.n_glwe, n = d.n;
   const size_t total = (size_t)ws * G;
   EncBatch b;
@@ -1212,22 +1316,29 @@ extern "C" int fheram_ram_encrypt_sk(fheram_ram* r, const uint8_t* data, const i
   b.keys.resize(8); b.word0.resize(1);
   fheram_source_tell(xa, b.keys.data(), (uint64_t*)&b.word0[0]);
   b.glwe_per_stream = (int)total;
-  // noise in the order of src/ram.rs:161-166 (sub-RAM major), every polynomial of every shard
-  std::vector<int8_t> all_noise(total * n);
-  fheram_source_noise_i8(xe, all_noise.data(), all_noise.size());
-  b.noise.resize((size_t)b.n_glwe * n); b.pt.resize((size_t)b.n_glwe * n); b.seq.resize(b.n_glwe);
+  // noise in the order of src/ram.rs:161-166 (sub-RAM major), every polynomial of every shard: one stream
+  DevBuf d_noise;
+  {
+    fheram_source* xes[1] = {xe};
+    int rc = sample_noise(c, xes, 1, total * n, d_noise);
+    if (rc) { d_noise.release(); return rc; }
+  }
+  b.pt.resize((size_t)b.n_glwe * n); b.seq.resize(b.n_glwe);
   for (int s = 0; s < ws; s++)
     for (int hp = 0; hp < r->n_local; hp++) {
       const int h = r->shard + r->n_shards * hp;
       const size_t jl = (size_t)s * r->n_local + hp, jg = (size_t)s * G + h;
       b.seq[jl] = (int)jg;
-      memcpy(&b.noise[jl * n], &all_noise[jg * n], n);
       for (int j = 0; j < n; j++) {
         const uint64_t addr = (uint64_t)h * n + j;
         b.pt[jl * n + j] = addr < p.max_addr ? (int8_t)data[addr * ws + s] : 0;  // src/ram.rs:364
       }
     }
-  TRY(run_encrypt(c, sk, b, r->data, c->ct_stride()));
+  {
+    int rc = run_encrypt(c, sk, b, d_noise, true, r->data, c->ct_stride());
+    d_noise.release();
+    if (rc) return rc;
+  }
   fheram_source_skip_words(xa, 2ull * d.size_ct * n * total);
   r->loaded = true;
   r->state = false;
@@ -1236,8 +1347,8 @@ extern "C" int fheram_ram_encrypt_sk(fheram_ram* r, const uint8_t* data, const i
 
 // Address::encrypt_sk (src/address.rs:86-109) for addresses [first, first + count) of a device address set.
 // n_sources = 1: all addresses draw from (xa[0], xe[0]) one after the other, as `count` calls of
-// fheram_encrypt_address would; n_sources = count: address i draws from (xa[i], xe[i]) and the noise is
-// sampled on host threads.  Raw GGSWs only: fheram_address_prepare makes them usable.
+// fheram_encrypt_address would; n_sources = count: address i draws from (xa[i], xe[i]).
+// Raw GGSWs only: fheram_address_prepare makes them usable.
 extern "C" int fheram_address_encrypt_sk(fheram_address* a, int first, int count, const uint32_t* values,
                                          const int64_t* sk, fheram_source* const* xa, fheram_source* const* xe,
                                          int n_sources) {
@@ -1248,6 +1359,11 @@ extern "C" int fheram_address_encrypt_sk(fheram_address* a, int first, int count
   CU(cudaSetDevice(c->device));
   const Derived& d = c->d;
   const int n = d.n, per = d.n_ggsw * d.dnum_ct * 2;
+  TRY(check_secret(sk, n));
+  for (int i = 0; i < n_sources; i++)
+    for (int j = 0; j < n_sources; j++)
+      if (xa[i] == xe[j] || (i != j && (xa[i] == xa[j] || xe[i] == xe[j])))
+        return fail(FHERAM_ERR_INVALID, "every stream needs its own Source");
   EncBatch b;
   b.n_glwe = count * per; b.size = d.size_addr; b.k_noise = c->params.k_addr;
   b.mono.resize(b.n_glwe);
@@ -1264,22 +1380,17 @@ extern "C" int fheram_address_encrypt_sk(fheram_address* a, int first, int count
   b.keys.resize((size_t)8 * n_sources); b.word0.resize(n_sources);
   for (int i = 0; i < n_sources; i++) fheram_source_tell(xa[i], &b.keys[8 * i], (uint64_t*)&b.word0[i]);
   b.glwe_per_stream = n_sources == 1 ? b.n_glwe : per;
-  b.noise.resize((size_t)b.n_glwe * n);
-  if (n_sources == 1) {
-    fheram_source_noise_i8(xe[0], b.noise.data(), b.noise.size());
-  } else {
-    unsigned nt = std::thread::hardware_concurrency();
-    nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
-    if ((int)nt > count) nt = count;
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; t++)
-      th.emplace_back([&, t]() {
-        for (int i = t; i < count; i += nt) fheram_source_noise_i8(xe[i], &b.noise[(size_t)i * per * n], (size_t)per * n);
-      });
-    for (auto& t : th) t.join();
+  DevBuf d_noise;
+  {
+    int rc = sample_noise(c, xe, n_sources, (size_t)b.n_glwe / n_sources * n, d_noise);
+    if (rc) { d_noise.release(); return rc; }
   }
   const long stride = (long)2 * d.size_addr * n;
-  TRY(run_encrypt(c, sk, b, a->raw + (size_t)first * d.n_ggsw * c->ggsw_raw_len(), stride));
+  {
+    int rc = run_encrypt(c, sk, b, d_noise, false, a->raw + (size_t)first * d.n_ggsw * c->ggsw_raw_len(), stride);
+    d_noise.release();
+    if (rc) return rc;
+  }
   for (int i = 0; i < n_sources; i++)
     fheram_source_skip_words(xa[i], 2ull * d.size_addr * n * (n_sources == 1 ? (uint64_t)b.n_glwe : (uint64_t)per));
   a->inv_ready = false;

@@ -14,7 +14,8 @@ struct EncArgs {
   int n_glwe, size;           // limbs per GLWE
   int nl, sh;                 // noise: limb nl += e << sh   (k_noise = (nl + 1) K - sh)
   const double2* sk_spec;     // [M] prepared secret (1/M folded in)
-  const signed char* noise;   // [n_glwe][N]
+  const signed char* noise;   // [n_glwe][N], or (noise_by_seq) indexed by stream * glwe_per_stream + seq[j]
+  int noise_by_seq;
   const signed char* pt;      // dense plaintext, one signed byte per coefficient, or null
   int pt_l, pt_sh;            //   limb pt_l += v << pt_sh   (encode at k_pt, src/ram.rs:364-368)
   const int* mono;            // per GLWE monomial +/- X^pos: pos | neg << 12 | limb << 16 | col << 24, or null
@@ -51,6 +52,67 @@ __device__ __forceinline__ void chacha20_block(const uint32_t* key, unsigned lon
 }
 #undef FHERAM_QR
 
+// Encryption noise on the device: sample k of a stream is client.cpp's fheram_source::gauss(3.2, 19.2) on the
+// stream words 4k .. 4k+3 (two 53-bit uniforms, Box-Muller cosine branch, rounded to the nearest integer), as
+// long as no earlier draw of the stream was rejected.  libm and CUDA agree on log / cos only to a few ulp, so
+// every sample whose value could round differently (within `guard` of a half-integer) is reported for the host
+// to recompute (kind 0), and every sample within `guard` of the rejection bound or beyond it marks its whole
+// stream for host sampling (kind 1).  With guard = 1e-9 that is about one report in 10^8 samples.
+struct NoiseArgs {
+  signed char* out;            // [n_streams][per_stream]
+  int n_streams;
+  long per_stream;             // multiple of 4
+  const uint32_t* keys;        // [n_streams][8]
+  const unsigned long long* word0;
+  double guard, bound_guard;   // widths of the two report bands (equal in production; tests widen them separately)
+  unsigned* n_flags;           // reports appended to flags[] (counted even beyond max_flags)
+  unsigned long long* flags;   // stream << 40 | kind << 39 | sample index
+  unsigned max_flags;
+};
+__global__ void __launch_bounds__(256) k_noise_sample(const NoiseArgs A) {
+  const long groups_per_stream = A.per_stream / 4;
+  const long n_groups = groups_per_stream * A.n_streams;
+  for (long gi = blockIdx.x * (long)blockDim.x + threadIdx.x; gi < n_groups; gi += (long)gridDim.x * blockDim.x) {
+    const int stream = (int)(gi / groups_per_stream);
+    const long k0 = 4 * (gi % groups_per_stream);
+    uint32_t key[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) key[i] = __ldg(A.keys + stream * 8 + i);
+    const unsigned long long w = A.word0[stream] + 4ull * k0;
+    const int r = (int)(w & 15);
+    uint32_t ww[32];
+    {
+      uint32_t o[16];
+      chacha20_block(key, w >> 4, o);
+#pragma unroll
+      for (int i = 0; i < 16; i++) ww[i] = o[i];
+      if (r) {
+        chacha20_block(key, (w >> 4) + 1, o);
+#pragma unroll
+        for (int i = 0; i < 16; i++) ww[16 + i] = o[i];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const unsigned long long x1 = (unsigned long long)ww[r + 4 * t] | ((unsigned long long)ww[r + 4 * t + 1] << 32);
+      const unsigned long long x2 = (unsigned long long)ww[r + 4 * t + 2] | ((unsigned long long)ww[r + 4 * t + 3] << 32);
+      const double u1 = ((double)(x1 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+      const double u2 = ((double)(x2 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+      const double z = sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2) * 3.2;
+      const double rz = round(z);  // half away from zero, as llround
+      int kind = -1;
+      if (!(fabs(z) < 19.2 - A.bound_guard)) kind = 1;
+      else if (0.5 - fabs(z - rz) < A.guard) kind = 0;
+      if (kind >= 0) {
+        const unsigned slot = atomicAdd(A.n_flags, 1u);
+        if (slot < A.max_flags)
+          A.flags[slot] = ((unsigned long long)stream << 40) | ((unsigned long long)kind << 39) | (unsigned long long)(k0 + t);
+      }
+      A.out[(size_t)stream * A.per_stream + k0 + t] = (signed char)(int)fmax(-127.0, fmin(127.0, rz));
+    }
+  }
+}
+
 // One CTA per GLWE (grid-stride).  Limbs from the least significant one up, so that the
 // normalization carry of each coefficient stays in a register.
 __global__ void __launch_bounds__(kThreads, 2) k_glwe_encrypt(const EncArgs A) {
@@ -65,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_glwe_encrypt(const EncArgs A) {
 #pragma unroll
     for (int i = 0; i < 8; i++) key_s[i] = __ldg(A.keys + stream * 8 + i);
     int* out = A.out + (size_t)j * A.ct_stride;
-    const signed char* noise = A.noise + (size_t)j * kN;
+    const signed char* noise = A.noise + (size_t)(A.noise_by_seq ? stream * A.glwe_per_stream + jl : j) * kN;
     const signed char* pt = A.pt ? A.pt + (size_t)j * kN : nullptr;
     int m_pos = -1, m_val = 0, m_limb = -1, m_col = 0;
     if (A.mono) {

@@ -247,7 +247,9 @@ int fheram_decrypt_word(const fheram_params *p, const int64_t *glwe, const int64
 
 /* ---- bulk encryption on the device.  For colocated client / server set-ups (tests,
  * benchmarks, loaders that hold the secret): the mask comes from the Source's ChaCha20 stream regenerated on
- * the GPU, the product with the secret and the normalization run on the GPU, the noise is drawn on the host.
+ * the GPU (k_glwe_encrypt), the product with the secret and the normalization run on the GPU; the noise is
+ * sampled on the GPU too (k_noise_sample) and the host re-draws the rare samples whose rounding or rejection
+ * could depend on libm's last bit (about one in 10^8).
  * Limb for limb what fheram_encrypt_ram / fheram_encrypt_address produce from the same Sources, and both
  * Sources are left where those calls would leave them. ---- */
 /* Ram::encrypt_sk (src/ram.rs:129-167, SubRam::encrypt_sk :334-380) straight into the device RAM (a
@@ -260,6 +262,8 @@ int fheram_ram_encrypt_sk(fheram_ram *r, const uint8_t *data, const int64_t *sk,
 int fheram_address_encrypt_sk(fheram_address *a, int first, int count, const uint32_t *values,
                               const int64_t *sk, fheram_source *const *xa, fheram_source *const *xe,
                               int n_sources);
+/* out = {noise draws sampled on the device, draws re-drawn by the host, streams sampled by the host} so far */
+int fheram_debug_encrypt_stats(fheram_ctx *ctx, uint64_t out[3]);
 
 #ifdef __cplusplus
 }

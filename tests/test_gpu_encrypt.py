@@ -3,8 +3,16 @@ fheram_address_encrypt_sk must give, limb for limb, what the CPU client side (cl
 Ram::encrypt_sk src/ram.rs:129-167, Address::encrypt_sk src/address.rs:86-109) gives from the same
 Sources, and leave both Sources at the same stream position.  The CPU client side is itself checked
 against the oracle in tests/test_abi.py::test_client_side_matches_oracle."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
 import numpy as np
 import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
 
 
 def _sources_agree(a, b):
@@ -70,7 +78,7 @@ def test_address_encrypt_sk_on_device_equals_client_side(built, max_addr):
     dev = fr.Address.encrypt_sk_gpu(params, values, sk, xa1, xe1)
     assert np.array_equal(dev.download_raw(), want)
     assert _sources_agree(xa0, xa1) and _sources_agree(xe0, xe1)
-    # one pair per address (host threads draw the noise)
+    # one pair per address
     want2 = np.concatenate([fr.Address.alloc(params).encrypt_sk(params, v, sk, fr.Source(100 + i), fr.Source(200 + i)).data
                             for i, v in enumerate(values)])
     xas = [fr.Source(100 + i) for i in range(len(values))]
@@ -112,3 +120,68 @@ def test_address_out_of_range_is_rejected_before_sources_move(built):
     with pytest.raises(fr.FheRamError):
         fr.Address.encrypt_sk_gpu(params, [1, 1 << 13], sk, xa, xe)
     assert _sources_agree(xa, fr.Source(1)) and _sources_agree(xe, fr.Source(2))
+
+
+_NOISE_SCRIPT = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+import fhe_ram_b200 as fr
+params = fr.Parameters.new(max_addr=1 << 13, word_size=2, k_pt=8)
+sk, _ = fr.gen_keys(params)
+data = fr.Source(5).fill_bytes(params.max_addr() * 2)
+ram0, ram1 = fr.Ram.new(params), fr.Ram.new(params)
+xa0, xe0, xa1, xe1 = fr.Source(21), fr.Source(22), fr.Source(21), fr.Source(22)
+want = ram0.encrypt_sk(data, sk, xa0, xe0)
+ram1.encrypt_sk_gpu(data, sk, xa1, xe1)
+ok = bool(np.array_equal(ram1.store(), want))
+ok &= [xe0.next_u32() for _ in range(4)] == [xe1.next_u32() for _ in range(4)]
+values = list(range(0, 8192, 683))
+want = np.concatenate([fr.Address.alloc(params).encrypt_sk(params, v, sk, fr.Source(100 + i), fr.Source(200 + i)).data
+                       for i, v in enumerate(values)])
+xes = [fr.Source(200 + i) for i in range(len(values))]
+dev = fr.Address.encrypt_sk_gpu(params, values, sk, [fr.Source(100 + i) for i in range(len(values))], xes)
+ok &= bool(np.array_equal(dev.download_raw(), want))
+ref = [fr.Source(200 + i) for i in range(len(values))]
+for i, v in enumerate(values):  # noise Sources end where the client side leaves them
+    fr.Address.alloc(params).encrypt_sk(params, v, sk, fr.Source(100 + i), ref[i])
+ok &= all(a.next_u32() == b.next_u32() for a, b in zip(xes, ref))
+print(json.dumps({"ok": ok, "streams": 1 + len(values), **params.encrypt_stats()}))
+"""
+
+
+def _run_noise_script(env_over):
+    env = dict(os.environ)
+    env.update(env_over)
+    r = subprocess.run([sys.executable, "-c", _NOISE_SCRIPT % str(ROOT)], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.gpu
+def test_noise_is_sampled_on_the_device_by_default(built):
+    st = _run_noise_script({})
+    assert st["ok"]
+    assert st["device_draws"] > 0 and st["host_streams"] == 0 and st["host_redraws"] <= 2, st
+
+
+@pytest.mark.gpu
+def test_host_redraws_of_reported_samples_keep_the_limbs(built):
+    # 0.1 % of the draws fall in a report band this wide: the host re-draws them one by one
+    st = _run_noise_script({"FHERAM_ENC_GUARD": "0.0005"})
+    assert st["ok"] and st["host_redraws"] > 100 and st["host_streams"] == 0, st
+
+
+@pytest.mark.gpu
+def test_streams_with_a_possible_rejection_are_sampled_by_the_host(built):
+    # report band of the rejection bound widened to |z| > 4.6 sigma: about 4 in 10 address streams (122 880 draws
+    # each) hold such a draw and go to the host sampler, the others stay on the device
+    st = _run_noise_script({"FHERAM_ENC_BOUND_GUARD": "4.48"})
+    assert st["ok"] and 0 < st["host_streams"] < st["streams"] and st["device_draws"] > 0, st
+
+
+@pytest.mark.gpu
+def test_host_only_noise_mode(built):
+    st = _run_noise_script({"FHERAM_ENC_NOISE": "host"})
+    assert st["ok"] and st["device_draws"] == 0 and st["host_streams"] == st["streams"], st
