@@ -405,16 +405,32 @@ def main():
         assert np.array_equal(r2.store(), cts), "device Ram::encrypt_sk != client side"
         r2.close()
         na = min(B, 256)
-        xas, xes = [fr.Source(1000 + j) for j in range(na)], [fr.Source(5000 + j) for j in range(na)]
-        t0 = time.perf_counter()
-        dev = fr.Address.encrypt_sk_gpu(params, idxs[:na], sk, xas, xes)
-        params.synchronize(); t_addr_gpu = time.perf_counter() - t0
-        assert np.array_equal(dev.download_raw().reshape(na, -1), addr_limbs[:na]), "device Address::encrypt_sk != client side"
-        dev.close()
+        vals = np.ascontiguousarray(idxs[:na], dtype=np.uint32)
+        stages = None
+        for rep in range(2):  # second pass: kernels loaded, allocator warm
+            xas, xes = [fr.Source(1000 + j) for j in range(na)], [fr.Source(5000 + j) for j in range(na)]
+            ha = (C.c_void_p * na)(*[x.h for x in xas])
+            he = (C.c_void_p * na)(*[x.h for x in xes])
+            params.synchronize(); t0 = time.perf_counter()
+            dev = fr.Address.device_alloc(params, na)
+            params.synchronize(); t1 = time.perf_counter()
+            api._check(api.lib().fheram_address_encrypt_sk(dev.h, 0, na, vals.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                           api._p(sk.data), ha, he, na))
+            params.synchronize(); t2 = time.perf_counter()
+            dev.prepare()
+            params.synchronize(); t3 = time.perf_counter()
+            stages = (t1 - t0, t2 - t1, t3 - t2)
+            if rep == 0:
+                assert np.array_equal(dev.download_raw().reshape(na, -1), addr_limbs[:na]), \
+                    "device Address::encrypt_sk != client side"
+            dev.close()
+        t_addr_gpu = stages[1]
         lat["client_side_encrypt"] = {
             "ram_glwe": int(ws * params.n_glwe()), "ram_cpu_s": round(t_ram_cpu, 3), "ram_gpu_s": round(t_ram_gpu, 4),
             "addresses": na, "address_cpu_per_s": round(B / t_addr, 1), "address_cpu_threads": threads,
             "address_gpu_per_s": round(na / t_addr_gpu, 1),
+            "address_gpu_stage_ms": {"device_alloc": round(stages[0] * 1e3, 2), "encrypt": round(stages[1] * 1e3, 2),
+                                     "prepare": round(stages[2] * 1e3, 2)},
             "noise": params.encrypt_stats(),
             "note": "GPU path: mask (ChaCha20), noise (Box-Muller on the same stream; the host re-draws the samples "
                     "whose rounding could depend on libm's last bit), product with the secret and normalization on "

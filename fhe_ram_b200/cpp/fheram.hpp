@@ -138,9 +138,8 @@ class Ram {  // src/ram.rs:25-29
   void encrypt_sk(const std::vector<uint8_t>& data, const GLWESecret& sk, Source& xa, Source& xe) {  // :129-167
     if (data.size() % p_.word_size() != 0) throw Panic(-1, "invalid data: data.len()%ram_chunks != 0");
     if (data.size() / p_.word_size() != p_.max_addr()) throw Panic(-1, "invalid data: data.len()/ram_chunks != max_addr");
-    std::vector<int64_t> cts(p_.word_size() * p_.n_glwe() * p_.glwe_len());
-    check(fheram_encrypt_ram(&p_.c, data.data(), sk.data.data(), xa.raw(), xe.raw(), cts.data()));
-    check(fheram_ram_load(h_, cts.data()));
+    // on the device, straight into the resident RAM: the limbs fheram_encrypt_ram + fheram_ram_load would install
+    check(fheram_ram_encrypt_sk(h_, data.data(), sk.data.data(), xa.raw(), xe.raw()));
   }
   std::vector<GLWE> read(Address& a, const EvaluationKeysPrepared& k) {  // :172-191
     std::vector<int64_t> out(p_.word_size() * p_.glwe_len());

@@ -63,6 +63,11 @@ extern "C" {
                          atk: *mut i64, tsk: *mut i64, inv: *mut i64) -> c_int;
     pub fn fheram_encrypt_ram(p: *const fheram_params, data: *const u8, sk: *const i64, xa: *mut fheram_source,
                               xe: *mut fheram_source, cts: *mut i64) -> c_int;
+    pub fn fheram_ram_encrypt_sk(r: *mut fheram_ram, data: *const u8, sk: *const i64, xa: *mut fheram_source,
+                                 xe: *mut fheram_source) -> c_int;
+    pub fn fheram_address_encrypt_sk(a: *mut fheram_address, first: c_int, count: c_int, values: *const u32,
+                                     sk: *const i64, xa: *const *mut fheram_source, xe: *const *mut fheram_source,
+                                     n_sources: c_int) -> c_int;
     pub fn fheram_encrypt_address(p: *const fheram_params, value: u32, sk: *const i64, xa: *mut fheram_source,
                                   xe: *mut fheram_source, ggsw: *mut i64) -> c_int;
     pub fn fheram_encrypt_word(p: *const fheram_params, value: u8, sk: *const i64, xa: *mut fheram_source,

@@ -125,10 +125,8 @@ impl Ram {
         let p = &self.params;
         assert!(data.len() % p.word_size() == 0, "invalid data: data.len()%ram_chunks != 0");
         assert!(data.len() / p.word_size() == p.max_addr(), "invalid data: data.len()/ram_chunks != max_addr");
-        let n = unsafe { p.word_size() * fheram_n_glwe_per_subram(&p.c) as usize * fheram_glwe_len(&p.c) };
-        let mut cts = vec![0i64; n];
-        check(unsafe { fheram_encrypt_ram(&p.c, data.as_ptr(), sk.0.as_ptr(), xa.0, xe.0, cts.as_mut_ptr()) });
-        check(unsafe { fheram_ram_load(self.h, cts.as_ptr()) });
+        // on the device, straight into the resident RAM (the limbs fheram_encrypt_ram + fheram_ram_load would install)
+        check(unsafe { fheram_ram_encrypt_sk(self.h, data.as_ptr(), sk.0.as_ptr(), xa.0, xe.0) });
     }
     fn split(&self, flat: Vec<i64>) -> Vec<GLWE> { flat.chunks(self.params.glwe_len()).map(|c| c.to_vec()).collect() }
     /// src/ram.rs:172-191
