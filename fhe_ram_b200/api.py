@@ -119,6 +119,8 @@ SIGNATURES = {
     "fheram_source_free": (None, [_V]),
     "fheram_source_next_u32": (C.c_uint32, [_V]),
     "fheram_source_fill_bytes": (None, [_V, _PU8, C.c_size_t]),
+    "fheram_source_position": (C.c_uint64, [_V]),
+    "fheram_source_skip": (None, [_V, C.c_uint64]),
     "fheram_secret_gen": (C.c_int, [_PP, _V, _P64]),
     "fheram_keygen": (C.c_int, [_PP, _P64, _V, _V, _P64, _P64, _P64]),
     "fheram_encrypt_ram": (C.c_int, [_PP, _PU8, _P64, _V, _V, _P64]),
@@ -298,6 +300,13 @@ class Source:
 
     def next_u32(self) -> int:
         return int(lib().fheram_source_next_u32(self.h))
+
+    def position(self) -> int:
+        """32-bit words drawn so far"""
+        return int(lib().fheram_source_position(self.h))
+
+    def skip(self, n_words: int):
+        lib().fheram_source_skip(self.h, int(n_words))
 
     def fill_bytes(self, n: int) -> np.ndarray:
         out = np.zeros(n, dtype=np.uint8)

@@ -101,6 +101,12 @@ void fheram_source_skip_words(fheram_source* s, uint64_t n) {
   s->pos = 16;
   if (wp % 16) { s->refill(); s->pos = (int)(wp % 16); }
 }
+extern "C" uint64_t fheram_source_position(const fheram_source* s) {
+  return s ? s->counter * 16 + (u64)s->pos - 16 : 0;
+}
+extern "C" void fheram_source_skip(fheram_source* s, uint64_t n_words) {
+  if (s) fheram_source_skip_words(s, n_words);
+}
 int8_t fheram_source_noise_at(const fheram_source* s, uint64_t word_offset) {
   fheram_source t = *s;
   fheram_source_skip_words(&t, word_offset);

@@ -226,6 +226,10 @@ fheram_source *fheram_source_new(const uint8_t seed[32]);
 void fheram_source_free(fheram_source *s);
 uint32_t fheram_source_next_u32(fheram_source *s);
 void fheram_source_fill_bytes(fheram_source *s, uint8_t *out, size_t n);
+/* position in the stream, in 32-bit words drawn so far, and a seek forward (the stream is counter based): what lets
+ * the device regenerate a Source's draws (fheram_ram_encrypt_sk) and a rank skip the draws of another rank */
+uint64_t fheram_source_position(const fheram_source *s);
+void fheram_source_skip(fheram_source *s, uint64_t n_words);
 /* GLWESecret::fill_ternary_prob(0.5): sk = n coefficients in {-1,0,1} */
 int fheram_secret_gen(const fheram_params *p, fheram_source *xs, int64_t *sk);
 /* EvaluationKeys::encrypt_sk (src/keys.rs:135-180) */

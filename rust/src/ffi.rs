@@ -58,6 +58,8 @@ extern "C" {
     pub fn fheram_ram_write(r: *mut fheram_ram, w: *const i64, a: *const fheram_address, k: *const fheram_keys) -> c_int;
     pub fn fheram_source_new(seed: *const u8) -> *mut fheram_source;
     pub fn fheram_source_free(s: *mut fheram_source);
+    pub fn fheram_source_position(s: *const fheram_source) -> u64;
+    pub fn fheram_source_skip(s: *mut fheram_source, n_words: u64);
     pub fn fheram_secret_gen(p: *const fheram_params, xs: *mut fheram_source, sk: *mut i64) -> c_int;
     pub fn fheram_keygen(p: *const fheram_params, sk: *const i64, xa: *mut fheram_source, xe: *mut fheram_source,
                          atk: *mut i64, tsk: *mut i64, inv: *mut i64) -> c_int;

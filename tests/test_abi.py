@@ -124,6 +124,28 @@ def test_address_encodes_negated_digits(built):
             assert nz[0] == 4096 - e and pt[0, nz[0]] == -1
 
 
+def test_source_position_and_skip(built):
+    """The Source is a counter-based stream: skipping n words equals drawing them, from any alignment to the 16-word
+    ChaCha20 block.  The device encryption path (fheram_ram_encrypt_sk / fheram_address_encrypt_sk) regenerates the
+    draws from (key, position) and then skips the Source over them."""
+    import fhe_ram_b200 as fr
+    rng = np.random.default_rng(1)
+    for pre in (0, 1, 2, 15, 16, 17, 31, 32, 33):
+        for n in (0, 1, 2, 14, 15, 16, 17, 30, 31, 32, 33, 1000, int(rng.integers(1, 50000))):
+            a, b = fr.Source(7), fr.Source(7)
+            for _ in range(pre):
+                a.next_u32(); b.next_u32()
+            for _ in range(n):
+                a.next_u32()
+            b.skip(n)
+            assert a.position() == b.position() == pre + n
+            assert [a.next_u32() for _ in range(35)] == [b.next_u32() for _ in range(35)], (pre, n)
+    # position counts the words of the byte and 64-bit draws as well (fill_bytes: one word per 4 bytes, rounded up)
+    s = fr.Source(3)
+    s.fill_bytes(10)
+    assert s.position() == 3
+
+
 @pytest.mark.skipif(any(os.path.exists(f"/dev/nvidia{i}") for i in range(8)), reason="GPU present")
 def test_no_cpu_fallback(built):
     """without a CUDA device the product path raises instead of computing elsewhere."""
