@@ -175,6 +175,7 @@ struct fheram_ctx {
   uint64_t launches = 0;
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
+  DevBuf enc_buf[12];  // operands of the encryption kernels, kept between calls (cudaFree synchronizes the device)
   uint64_t enc_stats[3] = {0, 0, 0};  // noise draws sampled on the device / patched by the host / streams resampled on the host
   DevBuf opbuf[3];  // op-level entry points
   DevBuf split_tmp[2];  // ping-pong ciphertexts of the column-split (latency) schedules
@@ -343,6 +344,7 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
+  for (auto& b : c->enc_buf) b.release();
   cudaFree(c->d_tw); cudaFree(c->d_tw16); cudaFree(c->d_err);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1185,8 +1187,8 @@ static int sample_noise(fheram_ctx* c, fheram_source* const* xe, int n_streams, 
   std::vector<uint32_t> keys((size_t)8 * n_streams);
   std::vector<unsigned long long> w0(n_streams);
   for (int s = 0; s < n_streams; s++) fheram_source_tell(xe[s], &keys[8 * s], (uint64_t*)&w0[s]);
-  DevBuf dk, dw, df, dn;
-  auto cleanup = [&]() { dk.release(); dw.release(); df.release(); dn.release(); };
+  DevBuf &dk = c->enc_buf[0], &dw = c->enc_buf[1], &df = c->enc_buf[2], &dn = c->enc_buf[3];
+  auto cleanup = [&]() {};
   int rc = 0;
 #define NZ_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define NZ_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
@@ -1245,11 +1247,9 @@ static int check_secret(const int64_t* sk, int n) {  // before any Source moves
 static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, const DevBuf& d_noise, bool noise_by_seq,
                        int* d_out, long stride) {
   const int n = c->d.n;
-  DevBuf skraw, skspec, pt, mono, seq, keys, word0;
-  auto cleanup = [&]() {
-    skraw.release(); skspec.release(); pt.release(); mono.release(); seq.release();
-    keys.release(); word0.release();
-  };
+  DevBuf &skraw = c->enc_buf[4], &skspec = c->enc_buf[5], &pt = c->enc_buf[6], &mono = c->enc_buf[7],
+         &seq = c->enc_buf[8], &keys = c->enc_buf[9], &word0 = c->enc_buf[10];
+  auto cleanup = [&]() {};
   int rc = 0;
 #define ENC_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define ENC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
@@ -1317,11 +1317,10 @@ extern "C" int fheram_ram_encrypt_sk(fheram_ram* r, const uint8_t* data, const i
   fheram_source_tell(xa, b.keys.data(), (uint64_t*)&b.word0[0]);
   b.glwe_per_stream = (int)total;
   // noise in the order of src/ram.rs:161-166 (sub-RAM major), every polynomial of every shard: one stream
-  DevBuf d_noise;
+  DevBuf& d_noise = c->enc_buf[11];
   {
     fheram_source* xes[1] = {xe};
-    int rc = sample_noise(c, xes, 1, total * n, d_noise);
-    if (rc) { d_noise.release(); return rc; }
+    TRY(sample_noise(c, xes, 1, total * n, d_noise));
   }
   b.pt.resize((size_t)b.n_glwe * n); b.seq.resize(b.n_glwe);
   for (int s = 0; s < ws; s++)
@@ -1334,11 +1333,7 @@ extern "C" int fheram_ram_encrypt_sk(fheram_ram* r, const uint8_t* data, const i
         b.pt[jl * n + j] = addr < p.max_addr ? (int8_t)data[addr * ws + s] : 0;  // src/ram.rs:364
       }
     }
-  {
-    int rc = run_encrypt(c, sk, b, d_noise, true, r->data, c->ct_stride());
-    d_noise.release();
-    if (rc) return rc;
-  }
+  TRY(run_encrypt(c, sk, b, d_noise, true, r->data, c->ct_stride()));
   fheram_source_skip_words(xa, 2ull * d.size_ct * n * total);
   r->loaded = true;
   r->state = false;
@@ -1380,17 +1375,10 @@ extern "C" int fheram_address_encrypt_sk(fheram_address* a, int first, int count
   b.keys.resize((size_t)8 * n_sources); b.word0.resize(n_sources);
   for (int i = 0; i < n_sources; i++) fheram_source_tell(xa[i], &b.keys[8 * i], (uint64_t*)&b.word0[i]);
   b.glwe_per_stream = n_sources == 1 ? b.n_glwe : per;
-  DevBuf d_noise;
-  {
-    int rc = sample_noise(c, xe, n_sources, (size_t)b.n_glwe / n_sources * n, d_noise);
-    if (rc) { d_noise.release(); return rc; }
-  }
+  DevBuf& d_noise = c->enc_buf[11];
+  TRY(sample_noise(c, xe, n_sources, (size_t)b.n_glwe / n_sources * n, d_noise));
   const long stride = (long)2 * d.size_addr * n;
-  {
-    int rc = run_encrypt(c, sk, b, d_noise, false, a->raw + (size_t)first * d.n_ggsw * c->ggsw_raw_len(), stride);
-    d_noise.release();
-    if (rc) return rc;
-  }
+  TRY(run_encrypt(c, sk, b, d_noise, false, a->raw + (size_t)first * d.n_ggsw * c->ggsw_raw_len(), stride));
   for (int i = 0; i < n_sources; i++)
     fheram_source_skip_words(xa[i], 2ull * d.size_addr * n * (n_sources == 1 ? (uint64_t)b.n_glwe : (uint64_t)per));
   a->inv_ready = false;
