@@ -21,6 +21,7 @@
 #include "kernels_ks5.cuh"
 #include "kernels_ks6.cuh"
 #include "kernels_ks7.cuh"
+#include "kernels_ext8.cuh"
 #include "kernels_enc.cuh"
 #include "client_internal.h"
 
@@ -228,6 +229,7 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks7<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_ks7<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
+  CU(cudaFuncSetAttribute(k_ext8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt8Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
@@ -672,18 +674,39 @@ static int inv_mod_2n(int g) {  // g odd, modulus 2N = 8192: g^(N-1) since the u
   for (int e = kN - 1; e; e >>= 1) { if (e & 1) r = r * b % (2 * kN); b = b * b % (2 * kN); }
   return (int)r;
 }
-// vmp_prepare of n_mat matrices; gal != 1 prepares phi_gal(matrix) (key-switch keys, see k_vmp)
+// external-product chains on k_ext8 (kernels_ext8.cuh, one ciphertext per SM on the two-exchange transform):
+// FHERAM_EXT8 = 0 off (k_ext3 / k_vmp and GGSWs prepared in their frequency order), 1 (default) every launch.
+// The knob also selects the frequency order in which GGSWs are prepared, so it must not change within a process.
+static int ext8_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_EXT8"); v = e ? atoi(e) : 1; }
+  return v;
+}
+// vmp_prepare of n_mat matrices; gal != 1 prepares phi_gal(matrix) (key-switch keys, see k_vmp);
+// order7: frequency order of the 16-point transform (k_prepare7: consumers k_ks7 / k_ext8)
 static int prepare(fheram_ctx* c, const int* raw, long raw_stride, double2* out, long out_stride,
-                   int n_mat, int rows, int cin, int lout, int gal = 1) {
+                   int n_mat, int rows, int cin, int lout, int gal = 1, bool order7 = false) {
   PrepArgs a;
   a.raw = raw; a.out = out; a.raw_stride = raw_stride; a.out_stride = out_stride;
   a.rows = rows; a.cin = cin; a.lout = lout; a.tw = c->tw;
   a.gal_inv = inv_mod_2n(gal);
-  int grid = n_mat * rows * cin * 2 * lout;
-  k_prepare<<<grid, kThreads, 0, c->stream>>>(a);
+  if (order7) {
+    Prep7Args pa;
+    pa.p = a; pa.tw16 = c->d_tw16;
+    pa.n_polys = n_mat * rows * cin * 2 * lout;
+    k_prepare7<<<(pa.n_polys + 1) / 2, 256, kPrep7Smem, c->stream>>>(pa);
+  } else {
+    int grid = n_mat * rows * cin * 2 * lout;
+    k_prepare<<<grid, kThreads, 0, c->stream>>>(a);
+  }
   c->launches++;
   CU(cudaGetLastError());
   return 0;
+}
+// CoordinatePrepared::prepare (src/coordinate_prepared.rs:104-116) of n_mat GGSWs, in the order the external-product kernel in use reads
+static int prepare_ggsw(fheram_ctx* c, const int* raw, double2* out, int n_mat) {
+  return prepare(c, raw, c->ggsw_raw_len(), out, c->ggsw_prep_len(), n_mat, c->d.dnum_ct, 2, c->d.size_addr, 1,
+                 ext8_mode() != 0);
 }
 
 // --------------------------------------------------------------------------------------
@@ -779,7 +802,7 @@ extern "C" int fheram_address_load_batch(fheram_ctx* c, const int64_t* ggsw, int
   CU(cudaMalloc(&a->prep, sizeof(double2) * nm * c->ggsw_prep_len()));
   TRY(upload_i64(c, ggsw, nm * c->ggsw_raw_len(), a->raw));
   // CoordinatePrepared::prepare, src/coordinate_prepared.rs:104-116
-  TRY(prepare(c, a->raw, c->ggsw_raw_len(), a->prep, c->ggsw_prep_len(), (int)nm, d.dnum_ct, 2, d.size_addr));
+  TRY(prepare_ggsw(c, a->raw, a->prep, (int)nm));
   CU(cudaStreamSynchronize(c->stream));
   *out = a;
   return 0;
@@ -850,8 +873,7 @@ extern "C" int fheram_address_prepare(fheram_address* a) {  // CoordinatePrepare
   if (!a) return fail(FHERAM_ERR_INVALID, "null argument");
   fheram_ctx* c = a->c;
   CU(cudaSetDevice(c->device));
-  return prepare(c, a->raw, c->ggsw_raw_len(), a->prep, c->ggsw_prep_len(), a->count * c->d.n_ggsw, c->d.dnum_ct,
-                 2, c->d.size_addr);
+  return prepare_ggsw(c, a->raw, a->prep, a->count * c->d.n_ggsw);
 }
 extern "C" int fheram_address_load(fheram_ctx* c, const int64_t* ggsw, fheram_address** out) {
   return fheram_address_load_batch(c, ggsw, 1, out);
@@ -880,6 +902,20 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
   a.n_steps = n_dig;
   for (int s = 0; s < n_dig; s++) a.mat[s] = mats + (size_t)s * c->ggsw_prep_len();
   a.mat_div = mat_div; a.mat_stride = mat_stride;
+  if (ext8_mode() != 0) {
+    if (n_items <= 0) return 0;
+    const int grid = n_items < c->sm_count ? n_items : c->sm_count;
+    size_t e0 = 0;
+    if (c->profile) e0 = prof_event(c);
+    k_ext8<<<grid, kExt8Threads, kExt8Smem, c->stream>>>(a, c->d_tw16);
+    if (c->profile) {
+      size_t e1 = prof_event(c);
+      c->ev_recs.push_back({KC_EXT, e0, e1, (uint64_t)n_items, (uint64_t)n_dig});
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
   if (ks3_mode() >= 2) return launch_ks2(c, k_ext3, a, KC_EXT, kExt3Smem);  // forced (kernel-variant tests)
   if (use_split(c, n_items)) {
     // narrow launch: one step per launch, two CTAs per ciphertext (one output column each),
@@ -1636,7 +1672,7 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
     CUC(cudaStreamWaitEvent(c->stream, s.copied, 0));
     k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
     c->launches++;
-    TRYC(prepare(c, s.a.raw, c->ggsw_raw_len(), s.a.prep, c->ggsw_prep_len(), nb * d.n_ggsw, d.dnum_ct, 2, d.size_addr));
+    TRYC(prepare_ggsw(c, s.a.raw, s.a.prep, nb * d.n_ggsw));
     TRYC(ram_local_stage(r, &s.a, 0, nb, k, false));
     TRYC(ram_finish_stage(r, (const int*)r->partial.p, nb, 0, nb, &s.a, 0, k, false));
     CUC(cudaEventRecord(s.freed, c->stream));
@@ -1753,7 +1789,7 @@ static int address_prepare_inv(fheram_address* a, const fheram_keys* k) {
     CU(cudaMalloc(&a->inv_prep, sizeof(double2) * (size_t)d.n_ggsw * c->ggsw_prep_len()));
   }
   TRY(ggsw_invert_device(c, k, a->raw, d.n_ggsw, a->inv_raw));
-  TRY(prepare(c, a->inv_raw, c->ggsw_raw_len(), a->inv_prep, c->ggsw_prep_len(), d.n_ggsw, d.dnum_ct, 2, d.size_addr));
+  TRY(prepare_ggsw(c, a->inv_raw, a->inv_prep, d.n_ggsw));
   a->inv_ready = true;
   return 0;
 }
@@ -1830,8 +1866,7 @@ extern "C" int fheram_coordinate_product(fheram_ctx* c, const int64_t* in, int n
   TRY(c->opbuf[2].ensure(sizeof(double2) * (size_t)n_ggsw * c->ggsw_prep_len()));
   TRY(upload_i64(c, in, (size_t)n * L, (int*)c->opbuf[0].p));
   TRY(upload_i64(c, ggsws, (size_t)n_ggsw * c->ggsw_raw_len(), (int*)c->opbuf[1].p));
-  TRY(prepare(c, (int*)c->opbuf[1].p, c->ggsw_raw_len(), (double2*)c->opbuf[2].p, c->ggsw_prep_len(),
-              n_ggsw, c->d.dnum_ct, 2, c->d.size_addr));
+  TRY(prepare_ggsw(c, (int*)c->opbuf[1].p, (double2*)c->opbuf[2].p, n_ggsw));
   TRY(run_ext_chain(c, n, (int*)c->opbuf[0].p, nullptr, 0, (int*)c->opbuf[0].p, (double2*)c->opbuf[2].p,
                     n_ggsw, 0, 0));
   return download_i64(c, (int*)c->opbuf[0].p, (size_t)n * L, out);

@@ -12,6 +12,7 @@
 // Output: bytes per clock and SM.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tile_stage_probe tile_stage_probe.cu
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 constexpr int kTile = 16384;                 // bytes
@@ -130,10 +131,12 @@ static void run(const char* name, const double2* set, int tiles_per_cta, long lo
   printf("%-52s %9lld cycles, %6.1f B/clk/SM (%s)\n", name, mx, 2.0 * tiles_per_cta * kTile / (double)mx, cudaGetErrorString(e));
 }
 
-int main() {
+int main(int argc, char** argv) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (argc > 1) sms = atoi(argv[1]);  // stream on fewer SMs: per-SM port limit or aggregate L2 limit?
+  printf("streaming on %d SMs\n", sms);
   double2* set; long long* c; double* s;
   cudaMalloc(&set, kSetBytes); cudaMalloc(&c, 1024 * 8); cudaMalloc(&s, 8);
   cudaMemset(set, 0, kSetBytes);
