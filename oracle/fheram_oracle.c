@@ -801,6 +801,24 @@ void orc_external_product(const orc_ctx *c, const int64_t *in, const int64_t *gg
   pmat_free(g);
 }
 
+/* n ciphertexts against ONE GGSW (BASELINE.json config 2), the GGSW prepared once; one ciphertext per thread */
+void orc_external_product_many(const orc_ctx *c, const int64_t *in, int n, const int64_t *ggsw, int64_t *out,
+                               int threads) {
+  pmat *g = pmat_prepare(c, ggsw, c->dnum_ct, 2, 2, c->size_addr);
+  const size_t len = orc_glwe_len(c);
+  (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads > 0 ? threads : 1)
+#endif
+  for (int i = 0; i < n; i++) {
+    i64 *tmp = (i64 *)malloc(sizeof(i64) * len);
+    memcpy(tmp, in + (size_t)i * len, sizeof(i64) * len);
+    glwe_external_product(c, out + (size_t)i * len, c->size_ct, tmp, c->size_ct, g);
+    free(tmp);
+  }
+  pmat_free(g);
+}
+
 /* ======================================================================================
  * GLWEPacker (Poulpy [spec], log_batch = 0): binary counter of log_n accumulators.
  * ==================================================================================== */
@@ -1353,14 +1371,25 @@ static int subram_read(const orc_ctx *c, const subram *sr, orc_packer *packer, c
   return 0;
 }
 
+/* Test-infrastructure knob: the sub-RAMs of one read / read_prepare_write / write are independent
+ * (ram.rs:187-190 maps over them sequentially), so the checker may run them on several threads to keep the
+ * BASELINE-size parity tests short.  Default 1 = the reference's sequential order; results do not depend on it. */
+static int g_ram_threads = 1;
+void orc_set_ram_threads(int n) { g_ram_threads = n > 0 ? n : 1; }
+
 int orc_ram_read(orc_ram *r, const int64_t *addr, const orc_keys *k, int64_t *out) {
   const orc_ctx *c = r->c; /* ram.rs:172-191 */
-  for (int s = 0; s < c->p.word_size; s++) {
+  for (int s = 0; s < c->p.word_size; s++)
     if (!r->sub[s].loaded) return -1; /* :182-185 */
+  int rc_all = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_ram_threads)
+#endif
+  for (int s = 0; s < c->p.word_size; s++) {
     int rc = subram_read(c, &r->sub[s], r->sub[s].packer, addr, k, out + (size_t)s * orc_glwe_len(c));
-    if (rc) return rc;
+    if (rc) rc_all = rc;
   }
-  return 0;
+  return rc_all;
 }
 
 int orc_ram_read_many(orc_ram *r, const int64_t *addrs, int n_reads, const orc_keys *k,
@@ -1420,12 +1449,17 @@ static int subram_rpw(const orc_ctx *c, subram *sr, const i64 *addr, const orc_k
 }
 int orc_ram_read_prepare_write(orc_ram *r, const int64_t *addr, const orc_keys *k, int64_t *out) {
   const orc_ctx *c = r->c; /* ram.rs:196-222 */
-  for (int s = 0; s < c->p.word_size; s++) {
+  for (int s = 0; s < c->p.word_size; s++)
     if (!r->sub[s].loaded) return -1;
+  int rc_all = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_ram_threads)
+#endif
+  for (int s = 0; s < c->p.word_size; s++) {
     int rc = subram_rpw(c, &r->sub[s], addr, k, out + (size_t)s * orc_glwe_len(c));
-    if (rc) return rc;
+    if (rc) rc_all = rc;
   }
-  return 0;
+  return rc_all;
 }
 
 int orc_ram_write(orc_ram *r, const int64_t *w, const int64_t *addr, const orc_keys *k) {
@@ -1434,21 +1468,29 @@ int orc_ram_write(orc_ram *r, const int64_t *w, const int64_t *addr, const orc_k
   const int n = c->n, n2 = c->n_coord, S = c->size_ct, ws = c->p.word_size;
   if (n2 > 2) return -5;
   for (int s = 0; s < ws; s++) if (!r->sub[s].state) return -3; /* ram.rs:555-558 */
-  i64 *tmp_a = (i64 *)malloc(sizeof(i64) * len);
   /* write_first_step (ram.rs:544-577) */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_ram_threads)
+#endif
   for (int s = 0; s < ws; s++) {
     subram *sr = &r->sub[s];
+    i64 *tmp_a = (i64 *)malloc(sizeof(i64) * len);
     i64 *to = n2 != 1 ? sr->tree[sr->n_tree - 1][0] : sr->data[0];   /* :565-569 */
     orc_trace(c, k, 0, c->log_n, to, tmp_a);                         /* :572 */
     glwe_sub_inplace(c, to, tmp_a, S);                               /* :574 */
     glwe_add_inplace(c, to, w + (size_t)s * len, S);                 /* :575 */
     glwe_normalize_inplace(c, to, S);                                /* :576 */
+    free(tmp_a);
   }
   pmat *g[16];
   for (int i = n2 - 2; i >= 0; i--) {                                /* :258 */
     coordinate_prepare_inv(c, k, addr, i + 1, g);                    /* :260-271 */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_ram_threads)
+#endif
     for (int s = 0; s < ws; s++) {                                   /* write_mid_step :579-632 */
       subram *sr = &r->sub[s];
+      i64 *tmp_a = (i64 *)malloc(sizeof(i64) * len);
       i64 **tree_hi = i == 0 ? sr->data : sr->tree[i - 1];           /* :599-604 */
       int n_hi = i == 0 ? c->n_glwe : sr->tree_size[i - 1];
       i64 **tree_lo = sr->tree[i];
@@ -1466,10 +1508,14 @@ int orc_ram_write(orc_ram *r, const int64_t *w, const int64_t *addr, const orc_k
           glwe_rotate_inplace(c, -1, ct_lo, S);                      /* :629 */
         }
       }
+      free(tmp_a);
     }
     coordinate_free(c, i + 1, g);
   }
   coordinate_prepare_inv(c, k, addr, 0, g);                          /* :278-289 */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_ram_threads)
+#endif
   for (int s = 0; s < ws; s++) {                                     /* write_last_step :634-649 */
     subram *sr = &r->sub[s];
     for (int h = 0; h < c->n_glwe; h++)
@@ -1477,6 +1523,5 @@ int orc_ram_write(orc_ram *r, const int64_t *w, const int64_t *addr, const orc_k
     sr->state = 0;                                                   /* :648 */
   }
   coordinate_free(c, 0, g);
-  free(tmp_a);
   return 0;
 }

@@ -154,6 +154,8 @@ void orc_ram_store(const orc_ram *r, int64_t *cts);
 void orc_ram_tree_store(const orc_ram *r, int64_t *cts /* [word_size] GLWE, tree.last()[0] */);
 int orc_ram_state(const orc_ram *r);
 /* return 0 ok, <0 = the reference's assert would panic */
+void orc_external_product_many(const orc_ctx *c, const int64_t *in, int n, const int64_t *ggsw, int64_t *out, int threads);
+void orc_set_ram_threads(int n); /* sub-RAMs of one call on n threads (checker speed only; default 1) */
 int orc_ram_read(orc_ram *r, const int64_t *addr, const orc_keys *k, int64_t *out);
 int orc_ram_read_prepare_write(orc_ram *r, const int64_t *addr, const orc_keys *k, int64_t *out);
 int orc_ram_write(orc_ram *r, const int64_t *w, const int64_t *addr, const orc_keys *k);

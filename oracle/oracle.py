@@ -99,6 +99,8 @@ class Oracle:
             "orc_ram_new": (V, [V]), "orc_ram_free": (None, [V]),
             "orc_ram_load": (None, [V, _P64]), "orc_ram_store": (None, [V, _P64]),
             "orc_ram_tree_store": (None, [V, _P64]), "orc_ram_state": (C.c_int, [V]),
+            "orc_set_ram_threads": (None, [C.c_int]),
+            "orc_external_product_many": (None, [V, _P64, C.c_int, _P64, _P64, C.c_int]),
             "orc_ram_read": (C.c_int, [V, _P64, V, _P64]),
             "orc_ram_read_prepare_write": (C.c_int, [V, _P64, V, _P64]),
             "orc_ram_write": (C.c_int, [V, _P64, _P64, V]),
@@ -221,6 +223,13 @@ class Oracle:
         self.lib.orc_external_product(self.ctx, _p(np.ascontiguousarray(glwe)), _p(np.ascontiguousarray(ggsw)), _p(out))
         return out
 
+    def external_product_many(self, glwes, ggsw, threads=1):
+        glwes = np.ascontiguousarray(glwes, dtype=np.int64)
+        n = glwes.size // self.glwe_len
+        out = np.zeros((n, self.glwe_len), dtype=np.int64)
+        self.lib.orc_external_product_many(self.ctx, _p(glwes.reshape(-1)), n, _p(np.ascontiguousarray(ggsw)), _p(out.reshape(-1)), threads)
+        return out
+
     def coordinate_product(self, glwe, ggsws, n):
         out = np.zeros(self.glwe_len, dtype=np.int64)
         self.lib.orc_coordinate_product(self.ctx, _p(np.ascontiguousarray(glwe)), _p(np.ascontiguousarray(ggsws)), n, _p(out))
@@ -300,6 +309,10 @@ class Oracle:
         out = np.zeros(self.word_size * self.glwe_len, dtype=np.int64)
         self.lib.orc_ram_tree_store(ram, _p(out))
         return out
+
+    def set_ram_threads(self, n: int):
+        """sub-RAMs of one read / read_prepare_write / write on n threads (same results; checker speed only)"""
+        self.lib.orc_set_ram_threads(int(n))
 
     def ram_read(self, ram, addr, keys):
         out = np.zeros(self.word_size * self.glwe_len, dtype=np.int64)
