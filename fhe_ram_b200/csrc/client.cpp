@@ -311,7 +311,7 @@ int check(const fheram_params* p) {
     fheram_set_error("bad parameters");
     return FHERAM_ERR_INVALID;
   }
-  return 0;
+  return fheram_params_check(p);  // digit tables, max_addr, word_size: shared with fheram_ctx_create
 }
 
 }  // namespace

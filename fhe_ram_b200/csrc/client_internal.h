@@ -17,3 +17,6 @@ int8_t fheram_source_noise_at(const fheram_source* s, uint64_t word_offset);
 // the n_ggsw monomials +/- X^pos an address value is encoded as (src/address.rs:102-108,
 // src/coordinate.rs:148-179); returns n_ggsw or a negative status
 int fheram_address_monomials(const fheram_params* p, uint32_t value, int32_t* pos, int32_t* sign);
+// range checks of every field the digit tables / size helpers index with (n_decomp <= 8, max_addr <= N^2, ...);
+// 0 or FHERAM_ERR_INVALID with fheram_last_error set
+int fheram_params_check(const fheram_params* p);

@@ -97,6 +97,27 @@ static int base2d(uint32_t value, const int32_t* base, int n_base, int32_t* lens
   return n_out;
 }
 
+// one validation for fheram_ctx_create, the size helpers and the client side (client.cpp): the digit tables of
+// fheram_params / Derived hold 8 entries per coordinate and 8 coordinates
+int fheram_params_check(const fheram_params* p) {
+  if (!p) return fail(FHERAM_ERR_INVALID, "null parameters");
+  if (p->log_n < 1 || p->log_n > 16 || p->base2k < 1 || p->base2k > 30)
+    return fail(FHERAM_ERR_INVALID, "bad log_n / base2k");
+  if (p->n_decomp < 1 || p->n_decomp > 8)
+    return fail(FHERAM_ERR_INVALID, "n_decomp must be in 1..8 (decomp_n[8])");
+  int sum = 0;
+  for (int i = 0; i < p->n_decomp; i++) {
+    if (p->decomp_n[i] < 1 || p->decomp_n[i] > p->log_n) return fail(FHERAM_ERR_INVALID, "decomp_n[%d] out of range", i);
+    sum += p->decomp_n[i];
+  }
+  if (sum != p->log_n) return fail(FHERAM_ERR_INVALID, "sum(decomp_n) != log_n (src/parameters.rs:168)");
+  if (p->max_addr < 1 || p->max_addr > (1ull << (2 * p->log_n)))
+    return fail(FHERAM_ERR_INVALID, "max_addr must be in 1..N^2 (the reference's read loop supports two coordinates)");
+  if (p->word_size < 1 || p->word_size > 16 || p->k_pt < 1 || p->k_pt > 16)
+    return fail(FHERAM_ERR_INVALID, "bad word_size / k_pt");
+  return 0;
+}
+
 static Derived derive(const fheram_params* p) {
   Derived d;
   memset(&d, 0, sizeof(d));
@@ -118,14 +139,15 @@ static Derived derive(const fheram_params* p) {
   return d;
 }
 
-extern "C" size_t fheram_glwe_len(const fheram_params* p) { Derived d = derive(p); return (size_t)2 * d.size_ct * d.n; }
-extern "C" size_t fheram_ggsw_len(const fheram_params* p) { Derived d = derive(p); return (size_t)d.dnum_ct * 4 * d.size_addr * d.n; }
-extern "C" size_t fheram_atk_len(const fheram_params* p) { Derived d = derive(p); return (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n; }
-extern "C" size_t fheram_evk_inv_len(const fheram_params* p) { Derived d = derive(p); return (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n; }
+extern "C" size_t fheram_glwe_len(const fheram_params* p) { if (fheram_params_check(p)) return 0; Derived d = derive(p); return (size_t)2 * d.size_ct * d.n; }
+extern "C" size_t fheram_ggsw_len(const fheram_params* p) { if (fheram_params_check(p)) return 0; Derived d = derive(p); return (size_t)d.dnum_ct * 4 * d.size_addr * d.n; }
+extern "C" size_t fheram_atk_len(const fheram_params* p) { if (fheram_params_check(p)) return 0; Derived d = derive(p); return (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n; }
+extern "C" size_t fheram_evk_inv_len(const fheram_params* p) { if (fheram_params_check(p)) return 0; Derived d = derive(p); return (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n; }
 extern "C" int fheram_n_trace_keys(const fheram_params* p) { return p->log_n; }
-extern "C" int fheram_n_ggsw(const fheram_params* p) { return derive(p).n_ggsw; }
-extern "C" int fheram_n_glwe_per_subram(const fheram_params* p) { return derive(p).n_glwe; }
+extern "C" int fheram_n_ggsw(const fheram_params* p) { return fheram_params_check(p) ? 0 : derive(p).n_ggsw; }
+extern "C" int fheram_n_glwe_per_subram(const fheram_params* p) { return fheram_params_check(p) ? 0 : derive(p).n_glwe; }
 extern "C" int fheram_base2d(const fheram_params* p, int32_t lens[8], int32_t digits[64]) {
+  if (fheram_params_check(p)) return FHERAM_ERR_INVALID;
   return base2d((uint32_t)p->max_addr, p->decomp_n, p->n_decomp, lens, digits);
 }
 static int64_t galois(int log_n, int i) {  // Poulpy GLWE::trace_galois_elements
@@ -254,13 +276,7 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
     return fail(FHERAM_ERR_INVALID,
                 "unsupported cryptographic parameters: kernels are built for log_n=12 base2k=17 "
                 "k_ct=51 k_addr=68 k_evk_trace=68 k_evk_ggsw_inv=85 (src/parameters.rs:11-18)");
-  if (p->word_size < 1 || p->word_size > 16 || p->max_addr < 1 || p->k_pt < 1 || p->k_pt > 16)
-    return fail(FHERAM_ERR_INVALID, "bad word_size / max_addr / k_pt");
-  {
-    int s = 0;
-    for (int i = 0; i < p->n_decomp; i++) s += p->decomp_n[i];
-    if (s != p->log_n) return fail(FHERAM_ERR_INVALID, "sum(decomp_n) != log_n (src/parameters.rs:168)");
-  }
+  TRY(fheram_params_check(p));
   Derived d = derive(p);
   if (d.n_coord > 2)
     return fail(FHERAM_ERR_INVALID, "max_addr > N^2: the reference's read loop only supports two coordinates");
@@ -340,9 +356,12 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   return 0;
 }
 
+static void wipe_secrets(fheram_ctx* c);
 extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  wipe_secrets(c);
   cudaStreamSynchronize(c->stream);
   c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
@@ -953,8 +972,12 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   }
   a.rot_mod = rot_mod; a.rot_mul = rot_mul; a.rot_const = rot_const; a.sign = sign;
   if (a.n_steps == 0) {
-    // no level to run: only the (feed-order) gather remains
-    if (!src_map) return fail(FHERAM_ERR_INVALID, "empty trace chain");
+    // no level to run (max_addr = N^2: every packer level is two-sided): only the (feed-order) gather remains
+    if (!src_map) {
+      if (src != dst)
+        CU(cudaMemcpyAsync(dst, src, sizeof(int) * (size_t)n_items * c->ct_stride(), cudaMemcpyDeviceToDevice, c->stream));
+      return 0;
+    }
     k_gather<<<c->sm_count * 8, 256, 0, c->stream>>>(dst, src, src_map, src_mod, n_items, c->ct_stride());
     c->launches++;
     CU(cudaGetLastError());
@@ -1052,6 +1075,8 @@ struct fheram_ram {
   int* data = nullptr;       // [word_size][n_local] GLWE   (SubRam::data, src/ram.rs:299)
   int* tree = nullptr;       // [word_size] GLWE            (SubRam::tree[0][0], src/ram.rs:300)
   bool state = false;        // src/ram.rs:302
+  bool rotated = false;      // rpw_local_device rotated SubRam::data in place and rpw_finish_device has not completed:
+                             // the reference does both inside one call (src/ram.rs:502-533), so no read may see this state
   bool loaded = false;
   int* feed_map = nullptr;   // device: [word_size*n_local] feed position -> data index
   DevBuf bufA, bufB;         // work arenas [B][word_size][n_local] GLWE
@@ -1136,6 +1161,7 @@ extern "C" int fheram_ram_load(fheram_ram* r, const int64_t* cts) {
   }
   r->loaded = true;
   r->state = false;
+  r->rotated = false;
   return 0;
 }
 extern "C" int fheram_ram_store(fheram_ram* r, int64_t* cts) {
@@ -1224,10 +1250,8 @@ static int sample_noise(fheram_ctx* c, fheram_source* const* xe, int n_streams, 
   std::vector<unsigned long long> w0(n_streams);
   for (int s = 0; s < n_streams; s++) fheram_source_tell(xe[s], &keys[8 * s], (uint64_t*)&w0[s]);
   DevBuf &dk = c->enc_buf[0], &dw = c->enc_buf[1], &df = c->enc_buf[2], &dn = c->enc_buf[3];
-  auto cleanup = [&]() {};
-  int rc = 0;
-#define NZ_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
-#define NZ_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+#define NZ_TRY(x) TRY(x)
+#define NZ_CU(x) CU(x)
   NZ_TRY(dk.ensure(keys.size() * sizeof(uint32_t)));
   NZ_TRY(dw.ensure(w0.size() * sizeof(unsigned long long)));
   NZ_TRY(df.ensure((size_t)max_flags * sizeof(unsigned long long)));
@@ -1266,7 +1290,6 @@ static int sample_noise(fheram_ctx* c, fheram_source* const* xe, int n_streams, 
   }
 #undef NZ_TRY
 #undef NZ_CU
-  cleanup();
   return 0;
 }
 extern "C" int fheram_debug_encrypt_stats(fheram_ctx* c, uint64_t out[3]) {
@@ -1280,15 +1303,20 @@ static int check_secret(const int64_t* sk, int n) {  // before any Source moves
     if (sk[i] < -1 || sk[i] > 1) return fail(FHERAM_ERR_INVALID, "secret key is not ternary");
   return 0;
 }
+// zero every device buffer that held secret-key material or PRNG state of an encryption call
+static void wipe_secrets(fheram_ctx* c) {
+  const int idx[] = {0, 1, 4, 5, 9, 10, 11};  // noise Source keys / positions, sk, sk spectrum, mask Source keys / positions, noise
+  for (int i : idx)
+    if (c->enc_buf[i].p) cudaMemsetAsync(c->enc_buf[i].p, 0, c->enc_buf[i].bytes, c->stream);
+}
 static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, const DevBuf& d_noise, bool noise_by_seq,
                        int* d_out, long stride) {
   const int n = c->d.n;
   DevBuf &skraw = c->enc_buf[4], &skspec = c->enc_buf[5], &pt = c->enc_buf[6], &mono = c->enc_buf[7],
          &seq = c->enc_buf[8], &keys = c->enc_buf[9], &word0 = c->enc_buf[10];
-  auto cleanup = [&]() {};
-  int rc = 0;
-#define ENC_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
-#define ENC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  // on any failure the secret material already on the device is wiped before returning
+#define ENC_TRY(x) do { int rc_ = (x); if (rc_) { wipe_secrets(c); cudaStreamSynchronize(c->stream); return rc_; } } while (0)
+#define ENC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { wipe_secrets(c); cudaStreamSynchronize(c->stream); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   {
     std::vector<int> s32((size_t)2 * n, 0);
     for (int i = 0; i < n; i++) s32[i] = (int)sk[i];
@@ -1296,6 +1324,8 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, cons
     ENC_TRY(skspec.ensure(sizeof(double2) * 2 * kM));
     ENC_CU(cudaMemcpyAsync(skraw.p, s32.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
     ENC_CU(cudaStreamSynchronize(c->stream));
+    volatile int* vs = s32.data();  // host staging copy of the secret
+    for (int i = 0; i < 2 * n; i++) vs[i] = 0;
     ENC_TRY(prepare(c, (const int*)skraw.p, 2 * n, (double2*)skspec.p, 2 * kM, 1, 1, 1, 1));
   }
   auto up = [&](DevBuf& d, const void* h, size_t bytes) -> int {
@@ -1326,10 +1356,12 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, cons
   k_glwe_encrypt<<<grid, kThreads, 0, c->stream>>>(a);
   c->launches++;
   ENC_CU(cudaGetLastError());
+  // the secret, its spectrum, the ChaCha20 keys of the Sources and the raw noise do not outlive the call: the
+  // context belongs to the evaluator (colocated client / server mode)
+  wipe_secrets(c);
   ENC_CU(cudaStreamSynchronize(c->stream));
 #undef ENC_TRY
 #undef ENC_CU
-  cleanup();
   return 0;
 }
 
@@ -1540,6 +1572,8 @@ static int check_read_args(fheram_ram* r, const fheram_address* addr, const fher
   if (!r->loaded) return fail(FHERAM_ERR_UNINIT, "unitialized memory: self.data.len()=0 (src/ram.rs:182-185)");
   if (r->state)
     return fail(FHERAM_ERR_STATE, "invalid call to Memory.read: internal state is true -> requires calling Memory.write (src/ram.rs:393-396)");
+  if (r->rotated)
+    return fail(FHERAM_ERR_STATE, "read_prepare_write did not complete (rpw_local_device without a successful rpw_finish_device): the RAM is rotated; finish it, then write");
   return 0;
 }
 
@@ -1716,6 +1750,7 @@ extern "C" int fheram_ram_read_finish_device(fheram_ram* r, const int32_t* d_gat
   if (first < 0 || count < 0 || first + count > n_total || addr_first < 0 ||
       addr_first + first + count > addr->count)
     return fail(FHERAM_ERR_INVALID, "bad read range");
+  TRY(check_read_args(r, addr, k));
   CU(cudaSetDevice(r->c->device));
   TRY(ram_finish_stage(r, d_gathered, n_total, first, count, addr, addr_first, k, false));
   *d_out = (const int32_t*)r->result.p;
@@ -1730,6 +1765,7 @@ extern "C" int fheram_ram_rpw_local_device(fheram_ram* r, const fheram_address* 
   TRY(check_read_args(r, addr, k));
   if (addr->count != 1) return fail(FHERAM_ERR_INVALID, "read_prepare_write takes a single address");
   CU(cudaSetDevice(r->c->device));
+  r->rotated = true;  // before the in-place product: a failure below must not leave a readable, rotated RAM
   TRY(ram_local_stage(r, addr, 0, 1, k, true));
   *d_partial = (const int32_t*)r->partial.p;
   return 0;
@@ -1738,8 +1774,13 @@ extern "C" int fheram_ram_rpw_finish_device(fheram_ram* r, const int32_t* d_gath
                                             const fheram_address* addr, const fheram_keys* k,
                                             const int32_t** d_out) {
   if (!r || !d_gathered || !addr || !k || !d_out) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (addr->c != r->c || k->c != r->c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
+  if (!r->loaded) return fail(FHERAM_ERR_UNINIT, "unitialized memory: self.data.len()=0 (src/ram.rs:206-209)");
+  if (!r->rotated || r->state) return fail(FHERAM_ERR_STATE, "rpw_finish_device without a preceding rpw_local_device");
+  if (addr->count != 1) return fail(FHERAM_ERR_INVALID, "read_prepare_write takes a single address");
   CU(cudaSetDevice(r->c->device));
   TRY(ram_finish_stage(r, d_gathered, 1, 0, 1, addr, 0, k, true));
+  r->rotated = false;
   r->state = true;  // src/ram.rs:533
   *d_out = (const int32_t*)r->result.p;
   return 0;

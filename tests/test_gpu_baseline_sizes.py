@@ -42,7 +42,9 @@ def _acceptance(s, keys, idx, batch_idxs):
         assert np.array_equal(ram.store(), s.orc.ram_store(oram)), "RAM limbs after read_prepare_write"
         assert np.array_equal(ram.tree_store(), s.orc.ram_tree_store(oram)), "tree limbs after read_prepare_write"
 
-        value = np.array([(7 * idx + 3 * i + 1) % 256 for i in range(ws)], dtype=np.uint8)
+        # bytes below 128: the example encodes the written byte unsigned (examples/fhe-ram.rs:196) but checks it as a
+        # signed byte (:165); at k_pt = 9 the two agree only on 0..127
+        value = np.array([(7 * idx + 3 * i + 1) % 128 for i in range(ws)], dtype=np.uint8)
         w = np.stack([fr.encrypt_glwe(p, int(v), s.sk) for v in value])      # :141-149
         ram.write(w, addr, keys)                                             # :152
         assert s.orc.ram_write(oram, w.reshape(-1), addr.data, s.okeys) == 0
@@ -84,3 +86,29 @@ def test_config2_ext_product_batch_4096_every_ciphertext(scenario):
     want = s.orc.external_product_many(cts, ggsw, 8)
     bad = [i for i in range(n) if not np.array_equal(got[i], want[i])]
     assert not bad, f"{len(bad)} of {n} ciphertexts differ, first {bad[:5]}"
+
+
+def test_max_addr_n_squared_2pow24(scenario, gpu_keys):
+    """max_addr = N^2 (n_glwe = N: every packer level is two-sided, no trace chain before the tree):
+    read against the oracle limb for limb, read_prepare_write / write / read-back at the decrypt level."""
+    s = scenario(1 << 24, 1, 8)
+    fr, p = s.fr, s.params
+    keys = gpu_keys(s)
+    ram = fr.Ram.new(p)
+    ram.load(s.cts)
+    oram = s.orc.ram_new(s.cts)
+    idx = 13371337 % (1 << 24)
+    addr = s.address(idx)
+    got = ram.read(addr, keys)
+    rc, want = s.orc.ram_read(oram, addr.data, s.okeys)
+    assert rc == 0 and np.array_equal(got, want), np.count_nonzero(got != want)
+    s.check_decrypt(got, idx)
+    s.check_decrypt(ram.read_prepare_write(addr, keys), idx)
+    w = np.stack([fr.encrypt_glwe(p, 77, s.sk)])
+    ram.write(w, addr, keys)
+    data2 = s.data.copy()
+    data2[idx] = 77
+    s.check_decrypt(ram.read(addr, keys), idx, data2)
+    other = (idx + 4097) % (1 << 24)
+    s.check_decrypt(ram.read(s.address(other), keys), other, data2)
+    ram.close()
