@@ -103,7 +103,13 @@ SIGNATURES = {
     "fheram_ram_write": (C.c_int, [_V, _P64, _V, _V]),
     "fheram_ram_read_batch": (C.c_int, [_V, _V, _V, _P64]),
     "fheram_ram_read_batch_host": (C.c_int, [_V, _P64, C.c_int, _V, _P64]),
+    "fheram_ram_read_batch_host_i32": (C.c_int, [_V, C.POINTER(C.c_int32), C.c_int, _V, C.POINTER(C.c_int32)]),
     "fheram_ram_read_batch_device": (C.c_int, [_V, _V, _V, _PV]),
+    "fheram_comm_unique_id": (C.c_int, [_PU8]),
+    "fheram_comm_init": (C.c_int, [_V, C.c_int, C.c_int, _PU8]),
+    "fheram_comm_destroy": (C.c_int, [_V]),
+    "fheram_comm_n_ranks": (C.c_int, [_V]),
+    "fheram_comm_rank": (C.c_int, [_V]),
     "fheram_download_glwe": (C.c_int, [_V, _V, C.c_int, _P64]),
     "fheram_ram_read_local_device": (C.c_int, [_V, _V, _V, _PV]),
     "fheram_ram_read_finish_device": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, C.c_int, _V, _PV]),
@@ -270,6 +276,22 @@ class Parameters:
         n = lib().fheram_ctx_profile_records(self.module(), max_n, cls, ms, it, st)
         names = ("ext", "trace", "combine2", "other")
         return [(names[cls[i]], ms[i], int(it[i]), int(st[i])) for i in range(max(n, 0))]
+
+    # ---- multi-GPU communicator (fheram_comm_*): NCCL inside the library, one rank per context ----
+    @staticmethod
+    def comm_unique_id() -> np.ndarray:
+        """rank 0: the 128-byte id the other ranks need (hand it over with MPI / a store / torch.distributed)"""
+        out = np.zeros(128, dtype=np.uint8)
+        _check(lib().fheram_comm_unique_id(out.ctypes.data_as(_PU8)))
+        return out
+
+    def comm_init(self, n_ranks: int, rank: int, uid: np.ndarray):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.size == 128
+        _check(lib().fheram_comm_init(self.module(), n_ranks, rank, uid.ctypes.data_as(_PU8)))
+
+    def comm_destroy(self):
+        _check(lib().fheram_comm_destroy(self.module()))
 
     def fp64_peak_tflops(self, reps: int = 5) -> float:
         v = C.c_double()
@@ -577,15 +599,20 @@ class Ram:
         return out[0]
 
     def write(self, w, address: Address, keys: EvaluationKeysPrepared) -> None:
-        """Ram::write (src/ram.rs:226-294); w = word_size GLWE (assert :243)."""
+        """Ram::write (src/ram.rs:226-294); w = word_size GLWE (assert :243).  Sharded RAM with a communicator:
+        rank 0's word is broadcast, the other ranks may pass None."""
+        if w is None:
+            _check(lib().fheram_ram_write(self.h, None, address.device(), keys.h))
+            return
         w = np.ascontiguousarray(w, dtype=np.int64).reshape(-1)
         if w.size != self.params.word_size() * self.params.glwe_len():
             raise FheRamError(-1, "assertion failed: w.len() == self.subrams.len()")
         _check(lib().fheram_ram_write(self.h, _p(w), address.device(), keys.h))
 
     def read_batch(self, addresses: Address, keys: EvaluationKeysPrepared) -> np.ndarray:
-        """n independent reads (BASELINE.json config 3): [n][word_size] GLWE."""
-        out = self._out(addresses.count)
+        """n independent reads (BASELINE.json config 3): [n][word_size] GLWE (sharded RAM with a communicator: this
+        rank's n / n_shards reads of the batch)."""
+        out = self._out(addresses.count // self.n_shards)
         _check(lib().fheram_ram_read_batch(self.h, addresses.device(), keys.h, _p(out)))
         return out
 
@@ -594,6 +621,16 @@ class Ram:
         out = self._out(n) if out is None else out
         _check(lib().fheram_ram_read_batch_host(self.h, _p(np.ascontiguousarray(addr_limbs, dtype=np.int64).reshape(-1)),
                                                 n, keys.h, _p(out.reshape(-1))))
+        return out
+
+    def read_batch_host_i32(self, addr_limbs: np.ndarray, n: int, keys: EvaluationKeysPrepared, out=None) -> np.ndarray:
+        """the same from the compact host format: int32 limbs in, int32 limbs out (half the PCIe bytes)"""
+        a = np.ascontiguousarray(addr_limbs, dtype=np.int32).reshape(-1)
+        if out is None:
+            out = np.zeros((n, self.params.word_size(), self.params.glwe_len()), dtype=np.int32)
+        P32 = C.POINTER(C.c_int32)
+        _check(lib().fheram_ram_read_batch_host_i32(self.h, a.ctypes.data_as(P32), n, keys.h,
+                                                    out.reshape(-1).ctypes.data_as(P32)))
         return out
 
     def read_batch_device(self, addresses: Address, keys: EvaluationKeysPrepared) -> int:

@@ -3,6 +3,7 @@
 // Mirrors (not copies) the control flow of the reference's src/ram.rs; every schedule step
 // cites the lines it reproduces.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -50,6 +51,13 @@ void fheram_set_error(const char* msg) { g_err = msg; }
     if (e_ != cudaSuccess)                                                            \
       return fail(FHERAM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x,            \
                   cudaGetErrorString(e_));                                            \
+  } while (0)
+#define NC(x)                                                                         \
+  do {                                                                                \
+    ncclResult_t e_ = (x);                                                            \
+    if (e_ != ncclSuccess)                                                            \
+      return fail(FHERAM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x,            \
+                  ncclGetErrorString(e_));                                            \
   } while (0)
 #define TRY(x)            \
   do {                    \
@@ -191,6 +199,9 @@ struct fheram_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
+  // multi-GPU: one context per rank, NCCL communicator over NVLink (fheram_comm_init)
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
   double2* d_tw = nullptr;  // tw6 | tw7c | tw8c | tw9 | tw10c
   double2* d_tw16 = nullptr;  // twiddles of the 16-point transform (kernels_ks7.cuh): [16][16] | [128][7]
   Twiddles tw;
@@ -363,6 +374,7 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   cudaStreamSynchronize(c->stream);
   wipe_secrets(c);
   cudaStreamSynchronize(c->stream);
+  if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
   c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
   for (auto& b : c->enc_buf) b.release();
@@ -379,6 +391,56 @@ extern "C" int fheram_ctx_synchronize(fheram_ctx* c) {
 }
 extern "C" void* fheram_ctx_stream(fheram_ctx* c) { return (void*)c->stream; }
 extern "C" uint64_t fheram_ctx_launch_count(const fheram_ctx* c) { return c->launches; }
+
+// ---- multi-GPU communicator (one rank per context) --------------------------------------
+// Rank 0 draws the id and hands it to the other ranks out of band (MPI_Bcast, a TCP store, a file: 128 bytes);
+// every rank then calls fheram_comm_init on its own context.  After that the calls on a RAM created with
+// fheram_ram_create_sharded(ctx, rank, n_ranks) do their own exchange steps (all-to-all of packed partials for reads,
+// all-gather for read_prepare_write, broadcast of the written word for write), all on the context's stream.
+extern "C" int fheram_comm_unique_id(uint8_t id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (!id) return fail(FHERAM_ERR_INVALID, "null argument");
+  ncclUniqueId u;
+  NC(ncclGetUniqueId(&u));
+  memcpy(id, &u, sizeof(u));
+  return 0;
+}
+extern "C" int fheram_comm_init(fheram_ctx* c, int n_ranks, int rank, const uint8_t id[128]) {
+  if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks || (n_ranks & (n_ranks - 1)))
+    return fail(FHERAM_ERR_INVALID, "n_ranks must be a power of two and 0 <= rank < n_ranks");
+  if (c->comm) return fail(FHERAM_ERR_INVALID, "communicator already initialised");
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  NC(ncclCommInitRank(&c->comm, n_ranks, u, rank));
+  c->n_ranks = n_ranks; c->rank = rank;
+  return 0;
+}
+extern "C" int fheram_comm_destroy(fheram_ctx* c) {
+  if (!c) return 0;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->comm) NC(ncclCommDestroy(c->comm));
+  c->comm = nullptr; c->n_ranks = 1; c->rank = 0;
+  return 0;
+}
+extern "C" int fheram_comm_n_ranks(const fheram_ctx* c) { return c ? c->n_ranks : 0; }
+extern "C" int fheram_comm_rank(const fheram_ctx* c) { return c ? c->rank : -1; }
+// all-to-all of equal blocks (count ints each) on the context stream: block r of `send` goes to rank r, block r of
+// `recv` comes from rank r.  Integer limbs only: never a floating-point reduction.
+static int all_to_all_i32(fheram_ctx* c, const int* send, int* recv, size_t count) {
+  NC(ncclGroupStart());
+  for (int r = 0; r < c->n_ranks; r++) {
+    NC(ncclSend(send + (size_t)r * count, count, ncclInt32, r, c->comm, c->stream));
+    NC(ncclRecv(recv + (size_t)r * count, count, ncclInt32, r, c->comm, c->stream));
+  }
+  NC(ncclGroupEnd());
+  return 0;
+}
+// a sharded RAM can run its own exchange steps when its shard layout is the communicator's
+static bool comm_matches(const fheram_ctx* c, int shard, int n_shards) {
+  return c->comm && c->n_ranks == n_shards && c->rank == shard;
+}
 
 // ---- measurement helpers ----------------------------------------------------------------
 extern "C" int fheram_ctx_profile(fheram_ctx* c, int enable) {
@@ -800,9 +862,11 @@ struct fheram_address {
   int count = 0;
   int* raw = nullptr;        // [count][n_ggsw] raw GGSW, int32
   double2* prep = nullptr;   // [count][n_ggsw] prepared GGSW
-  int* inv_raw = nullptr;    // [n_ggsw] GGSW(X^+digit), built lazily by write
-  double2* inv_prep = nullptr;
-  bool inv_ready = false;
+  // CoordinatePrepared::prepare_inv of every digit (src/ram.rs:260-271,278-289): a cache of the address handle,
+  // built by read_prepare_write (off the critical path of the write that follows) or lazily by write
+  mutable int* inv_raw = nullptr;    // [n_ggsw] GGSW(X^+digit)
+  mutable double2* inv_prep = nullptr;
+  mutable bool inv_ready = false;
   // asynchronous slice upload (multi-GPU host-buffer pipeline): int64 staging, copy-stream events
   long long* stage = nullptr;
   size_t stage_cap = 0;
@@ -845,6 +909,7 @@ extern "C" int fheram_address_upload_slice(fheram_address* a, const int64_t* ggs
   fheram_ctx* c = a->c;
   CU(cudaSetDevice(c->device));
   const size_t per = (size_t)c->d.n_ggsw * c->ggsw_raw_len();
+  a->inv_ready = false;
   return upload_i64(c, ggsw, (size_t)count * per, a->raw + (size_t)first * per);
 }
 // Asynchronous variant for pipelines: host -> device copy and int64 -> int32 conversion run on the
@@ -865,6 +930,7 @@ extern "C" int fheram_address_upload_slice_async(fheram_address* a, const int64_
     CU(cudaMalloc(&a->stage, sizeof(long long) * n));
     a->stage_cap = n;
   }
+  a->inv_ready = false;
   if (!a->uploaded) CU(cudaEventCreateWithFlags(&a->uploaded, cudaEventDisableTiming));
   if (a->released_valid) CU(cudaStreamWaitEvent(c->copy_stream, a->released, 0));
   CU(cudaMemcpyAsync(a->stage, ggsw, sizeof(long long) * n, cudaMemcpyHostToDevice, c->copy_stream));
@@ -1083,7 +1149,10 @@ struct fheram_ram {
   DevBuf partial;            // [B][word_size] packed partials
   DevBuf result;             // [B][word_size] results
   DevBuf wbuf;               // uploaded write words
+  DevBuf wstage;             // their int64 staging
   DevBuf all;                // results of a chunked batched read
+  DevBuf xchg;               // sharded: partials received from the other ranks, [n_shards][reads][word_size]
+  DevBuf part_all;           // sharded, device-resident batch: partials of every read before the exchange
   struct HostPipe {          // fheram_ram_read_batch_host: double-buffered upload pipeline
     struct Set { long long* stage = nullptr; fheram_address a; cudaEvent_t copied = nullptr, freed = nullptr; };
     Set sets[2];
@@ -1126,7 +1195,7 @@ extern "C" int fheram_ram_destroy(fheram_ram* r) {
   if (!r) return 0;
   cudaSetDevice(r->c->device);
   cudaFree(r->data); cudaFree(r->tree); cudaFree(r->feed_map);
-  r->bufA.release(); r->bufB.release(); r->partial.release(); r->result.release(); r->wbuf.release(); r->all.release();
+  r->bufA.release(); r->bufB.release(); r->partial.release(); r->result.release(); r->wbuf.release(); r->wstage.release(); r->all.release(); r->xchg.release(); r->part_all.release();
   for (auto& s : r->pipe.sets) {
     cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
     s.a.raw = nullptr; s.a.prep = nullptr;
@@ -1589,12 +1658,53 @@ static int batch_chunk(const fheram_ram* r) {
   return ch;
 }
 
+// Sharded RAM with a communicator: addr holds the WHOLE batch (B addresses, the same on every rank, B a multiple of
+// n_ranks); rank q finishes reads [q B / G, (q + 1) B / G) and *d_out points at those B / G results.
+static int read_batch_device_sharded(fheram_ram* r, const fheram_address* addr, const fheram_keys* k,
+                                     const int32_t** d_out) {
+  fheram_ctx* c = r->c;
+  const int G = r->n_shards, B = addr->count, ws = c->params.word_size;
+  const long L = c->ct_stride();
+  if (B % G) return fail(FHERAM_ERR_INVALID, "batch must be a multiple of the number of ranks");
+  const int mine = B / G;
+  const int chunk = batch_chunk(r);
+  TRY(r->part_all.ensure(sizeof(int) * (size_t)B * ws * L));
+  TRY(r->xchg.ensure(sizeof(int) * (size_t)B * ws * L));
+  for (int b0 = 0; b0 < B; b0 += chunk) {          // local stage: rotate + pack the own polynomials for every read
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    TRY(ram_local_stage(r, addr, b0, nb, k, false));
+    CU(cudaMemcpyAsync((int*)r->part_all.p + (size_t)b0 * ws * L, r->partial.p, sizeof(int) * (size_t)nb * ws * L,
+                       cudaMemcpyDeviceToDevice, c->stream));
+  }
+  // one exchange step: block q of the partials (reads of rank q) goes to rank q
+  TRY(all_to_all_i32(c, (const int*)r->part_all.p, (int*)r->xchg.p, (size_t)mine * ws * L));
+  if (mine <= chunk) {
+    TRY(ram_finish_stage(r, (const int*)r->xchg.p, mine, 0, mine, addr, r->shard * mine, k, false));
+    *d_out = (const int32_t*)r->result.p;
+    return 0;
+  }
+  TRY(r->all.ensure(sizeof(int) * (size_t)mine * ws * L));
+  for (int f = 0; f < mine; f += chunk) {
+    const int nb = mine - f < chunk ? mine - f : chunk;
+    TRY(ram_finish_stage(r, (const int*)r->xchg.p, mine, f, nb, addr, r->shard * mine, k, false));
+    CU(cudaMemcpyAsync((int*)r->all.p + (size_t)f * ws * L, r->result.p, sizeof(int) * (size_t)nb * ws * L,
+                       cudaMemcpyDeviceToDevice, c->stream));
+  }
+  *d_out = (const int32_t*)r->all.p;
+  return 0;
+}
+
 extern "C" int fheram_ram_read_batch_device(fheram_ram* r, const fheram_address* addr,
                                             const fheram_keys* k, const int32_t** d_out) {
   TRY(check_read_args(r, addr, k));
-  if (r->n_shards != 1) return fail(FHERAM_ERR_INVALID, "sharded RAM: use read_local_device / read_finish_device");
+  if (!d_out) return fail(FHERAM_ERR_INVALID, "null argument");
   fheram_ctx* c = r->c;
   CU(cudaSetDevice(c->device));
+  if (r->n_shards != 1) {
+    if (!comm_matches(c, r->shard, r->n_shards))
+      return fail(FHERAM_ERR_INVALID, "sharded RAM: call fheram_comm_init(ctx, n_shards, shard, id) first, or use read_local_device / read_finish_device");
+    return read_batch_device_sharded(r, addr, k, d_out);
+  }
   const int B = addr->count, ws = c->params.word_size;
   const long L = c->ct_stride();
   const int chunk = batch_chunk(r);
@@ -1621,7 +1731,8 @@ extern "C" int fheram_ram_read_batch(fheram_ram* r, const fheram_address* addr, 
   if (!out) return fail(FHERAM_ERR_INVALID, "null argument");
   const int32_t* d = nullptr;
   TRY(fheram_ram_read_batch_device(r, addr, k, &d));
-  return download_i64(r->c, d, (size_t)addr->count * r->c->params.word_size * r->c->ct_stride(), out);
+  // sharded: this rank's slice of the results (reads [shard B / G, (shard + 1) B / G))
+  return download_i64(r->c, d, (size_t)(addr->count / r->n_shards) * r->c->params.word_size * r->c->ct_stride(), out);
 }
 extern "C" int fheram_ram_read(fheram_ram* r, const fheram_address* addr, const fheram_keys* k, int64_t* out) {
   if (addr && addr->count != 1) return fail(FHERAM_ERR_INVALID, "fheram_ram_read takes a single address");
@@ -1629,23 +1740,33 @@ extern "C" int fheram_ram_read(fheram_ram* r, const fheram_address* addr, const 
 }
 
 // Pipelined end-to-end batched read from HOST buffers (the reference-facing call for a batch):
-// addresses arrive as int64 limbs in host memory, results leave as int64 limbs.  Chunks of
-// addresses are double-buffered: the H2D copy of chunk k+1 runs on a copy stream while chunk k is
-// converted, prepared (CoordinatePrepared::prepare) and read on the compute stream.
-extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_host, int n,
-                                          const fheram_keys* k, int64_t* out_host) {
+// addresses arrive as limbs in host memory, results leave as limbs.  Host formats: int64 limbs (Poulpy's VecZnx,
+// elem_bytes 8) or the same limbs as int32 (elem_bytes 4: half the PCIe bytes, no conversion pass).
+// Chunks of addresses are double-buffered: the H2D copy of chunk k+1 runs on a copy stream while chunk k is
+// prepared (CoordinatePrepared::prepare) and read on the compute stream, and the results of chunk k-1 go back on a
+// third stream.
+// Sharded RAM (fheram_comm_init done): every rank passes ITS n addresses and receives ITS n results; the global batch
+// is the concatenation over ranks.  Per chunk: each rank uploads and prepares only its own addresses, the prepared
+// GGSWs are all-gathered over NVLink (NCCL, in place), every rank rotates + packs its own polynomials for all
+// n_ranks * nb reads of the chunk, the packed partials are exchanged with one all-to-all, and each rank finishes its
+// own nb reads (top log2 n_ranks packer levels, second coordinate, trace).
+static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_bytes, int n, const fheram_keys* k,
+                                void* out_host, int out_bytes) {
   if (!r || !ggsw_host || !k || !out_host || n < 1) return fail(FHERAM_ERR_INVALID, "bad argument");
   if (k->c != r->c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
   if (!r->loaded) return fail(FHERAM_ERR_UNINIT, "unitialized memory: self.data.len()=0 (src/ram.rs:182-185)");
-  if (r->state) return fail(FHERAM_ERR_STATE, "invalid call to Memory.read: internal state is true (src/ram.rs:393-396)");
-  if (r->n_shards != 1) return fail(FHERAM_ERR_INVALID, "sharded RAM: use the *_device entry points");
+  if (r->state || r->rotated) return fail(FHERAM_ERR_STATE, "invalid call to Memory.read: internal state is true (src/ram.rs:393-396)");
   fheram_ctx* c = r->c;
+  const int G = r->n_shards;
+  if (G != 1 && !comm_matches(c, r->shard, G))
+    return fail(FHERAM_ERR_INVALID, "sharded RAM: call fheram_comm_init(ctx, n_shards, shard, id) first, or use the *_device halves");
   CU(cudaSetDevice(c->device));
   const Derived& d = c->d;
   const int ws = c->params.word_size;
   const long L = c->ct_stride();
-  const size_t per_addr = (size_t)d.n_ggsw * c->ggsw_raw_len();  // limbs per address
-  int chunk = batch_chunk(r);
+  const size_t per_addr = (size_t)d.n_ggsw * c->ggsw_raw_len();                   // limbs per address
+  const size_t prep_addr = (size_t)d.n_ggsw * c->ggsw_prep_len() * sizeof(double2); // prepared bytes per address
+  int chunk = batch_chunk(r);   // reads per rank and chunk: the local stage handles G * chunk reads of 1 / G of the RAM
   if (chunk > n) chunk = n;
   // staging buffers, events and the copy stream are created once per RAM handle and reused
   // (cudaMalloc / cudaFree of gigabytes per call cost more than the copies they serve)
@@ -1659,6 +1780,7 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
   };
 #define TRYC(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define CUC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+#define NCC(x) do { ncclResult_t e_ = (x); if (e_ != ncclSuccess) { cleanup(); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, ncclGetErrorString(e_)); } } while (0)
   if (!hp.copy_stream) CU(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
   if (!hp.down_stream) CU(cudaStreamCreateWithFlags(&hp.down_stream, cudaStreamNonBlocking));
   if (hp.cap < chunk) {
@@ -1666,9 +1788,9 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
       cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
       s.stage = nullptr; s.a.raw = nullptr; s.a.prep = nullptr;
       s.a.c = c;
-      CU(cudaMalloc(&s.stage, sizeof(long long) * chunk * per_addr));
-      CU(cudaMalloc(&s.a.raw, sizeof(int) * chunk * per_addr));
-      CU(cudaMalloc(&s.a.prep, sizeof(double2) * (size_t)chunk * d.n_ggsw * c->ggsw_prep_len()));
+      CU(cudaMalloc(&s.stage, sizeof(long long) * chunk * per_addr));       // int64 staging of the own slice
+      CU(cudaMalloc(&s.a.raw, sizeof(int) * chunk * per_addr));             // raw limbs of the own slice
+      CU(cudaMalloc(&s.a.prep, (size_t)G * chunk * prep_addr));             // prepared GGSWs of every rank's slice
       if (!s.copied) CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
       if (!s.freed) CU(cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming));
     }
@@ -1681,18 +1803,22 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
     }
     hp.cap = chunk;
   }
+  if (G > 1) TRYC(r->xchg.ensure(sizeof(int) * (size_t)G * chunk * ws * L));
   Set* sets = hp.sets;
   cudaStream_t copy_stream = hp.copy_stream;
   // chunk boundaries: the first chunks are small (their upload is not overlapped with anything), then full size
   std::vector<int> start;
-  for (int b = 0, sz = chunk >= 64 ? 16 : chunk; b < n; b += sz, sz = sz * 2 < chunk ? sz * 2 : chunk) start.push_back(b);
+  for (int b = 0, sz = chunk >= 64 ? 16 : (chunk >= 8 ? chunk / 4 : chunk); b < n; b += sz, sz = sz * 2 < chunk ? sz * 2 : chunk) start.push_back(b);
   start.push_back(n);
   const int n_chunks = (int)start.size() - 1;
+  const char* in = (const char*)ggsw_host;
+  char* out = (char*)out_host;
   auto issue_copy = [&](int ci) -> int {
     Set& s = sets[ci & 1];
     const int b0 = start[ci], nb = start[ci + 1] - b0;
     if (ci >= 2) CU(cudaStreamWaitEvent(copy_stream, s.freed, 0));
-    CU(cudaMemcpyAsync(s.stage, ggsw_host + (size_t)b0 * per_addr, sizeof(long long) * nb * per_addr,
+    void* dst = in_bytes == 8 ? (void*)s.stage : (void*)s.a.raw;  // int32 limbs land where the prepare kernel reads them
+    CU(cudaMemcpyAsync(dst, in + (size_t)b0 * per_addr * in_bytes, (size_t)nb * per_addr * in_bytes,
                        cudaMemcpyHostToDevice, copy_stream));
     CU(cudaEventRecord(s.copied, copy_stream));
     return 0;
@@ -1702,23 +1828,38 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
     if (ci + 1 < n_chunks) TRYC(issue_copy(ci + 1));
     Set& s = sets[ci & 1];
     const int b0 = start[ci], nb = start[ci + 1] - b0;
-    s.a.count = nb;
+    s.a.count = G * nb;
     CUC(cudaStreamWaitEvent(c->stream, s.copied, 0));
-    k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
-    c->launches++;
-    TRYC(prepare_ggsw(c, s.a.raw, s.a.prep, nb * d.n_ggsw));
-    TRYC(ram_local_stage(r, &s.a, 0, nb, k, false));
-    TRYC(ram_finish_stage(r, (const int*)r->partial.p, nb, 0, nb, &s.a, 0, k, false));
+    if (in_bytes == 8) {
+      k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
+      c->launches++;
+    }
+    // prepare the own nb addresses into block `shard` of the chunk's prepared set, then gather the other blocks
+    double2* own = s.a.prep + (size_t)r->shard * nb * d.n_ggsw * c->ggsw_prep_len();
+    TRYC(prepare_ggsw(c, s.a.raw, own, nb * d.n_ggsw));
+    if (G > 1) NCC(ncclAllGather(own, s.a.prep, (size_t)nb * prep_addr, ncclChar, c->comm, c->stream));
+    TRYC(ram_local_stage(r, &s.a, 0, G * nb, k, false));
+    const int* gathered = (const int*)r->partial.p;
+    if (G > 1) {
+      TRYC(all_to_all_i32(c, (const int*)r->partial.p, (int*)r->xchg.p, (size_t)nb * ws * L));
+      gathered = (const int*)r->xchg.p;
+    }
+    TRYC(ram_finish_stage(r, gathered, nb, 0, nb, &s.a, r->shard * nb, k, false));
     CUC(cudaEventRecord(s.freed, c->stream));
-    // results: widen on the compute stream, download on a third stream (overlaps the next chunk's reads)
+    // results: widened on the compute stream if the host wants int64, downloaded on a third stream (overlaps the
+    // next chunk's reads)
     long long* os = hp.out_stage[ci & 1];
     if (ci >= 2) CUC(cudaStreamWaitEvent(c->stream, hp.out_done[ci & 1], 0));
-    k_i32_to_i64<<<c->sm_count * 4, 256, 0, c->stream>>>((const int*)r->result.p, os, (size_t)nb * ws * L);
-    c->launches++;
+    const size_t n_res = (size_t)nb * ws * L;
+    if (out_bytes == 8) {
+      k_i32_to_i64<<<c->sm_count * 4, 256, 0, c->stream>>>((const int*)r->result.p, os, n_res);
+      c->launches++;
+    } else {
+      CUC(cudaMemcpyAsync(os, r->result.p, sizeof(int) * n_res, cudaMemcpyDeviceToDevice, c->stream));
+    }
     CUC(cudaEventRecord(hp.out_ready[ci & 1], c->stream));
     CUC(cudaStreamWaitEvent(hp.down_stream, hp.out_ready[ci & 1], 0));
-    CUC(cudaMemcpyAsync(out_host + (size_t)b0 * ws * L, os, sizeof(long long) * (size_t)nb * ws * L,
-                        cudaMemcpyDeviceToHost, hp.down_stream));
+    CUC(cudaMemcpyAsync(out + (size_t)b0 * ws * L * out_bytes, os, n_res * out_bytes, cudaMemcpyDeviceToHost, hp.down_stream));
     CUC(cudaEventRecord(hp.out_done[ci & 1], hp.down_stream));
   }
   CUC(cudaStreamSynchronize(c->stream));
@@ -1728,11 +1869,21 @@ extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_hos
   cleanup();
 #undef TRYC
 #undef CUC
+#undef NCC
   if (err) {
     cudaMemset(c->d_err, 0, sizeof(int));
     return fail(FHERAM_ERR_RANGE, "limb outside +-2^30: ciphertext limbs must be (nearly) normalised");
   }
   return 0;
+}
+extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_host, int n, const fheram_keys* k,
+                                          int64_t* out_host) {
+  return read_batch_host_impl(r, ggsw_host, 8, n, k, out_host, 8);
+}
+// compact host format: the same limbs as int32 (normalised digits fit 17 bits), addresses and results
+extern "C" int fheram_ram_read_batch_host_i32(fheram_ram* r, const int32_t* ggsw_host, int n, const fheram_keys* k,
+                                              int32_t* out_host) {
+  return read_batch_host_impl(r, ggsw_host, 4, n, k, out_host, 4);
 }
 
 extern "C" int fheram_ram_read_local_device(fheram_ram* r, const fheram_address* addr,
@@ -1757,6 +1908,7 @@ extern "C" int fheram_ram_read_finish_device(fheram_ram* r, const int32_t* d_gat
   return 0;
 }
 
+static int address_prepare_inv(const fheram_address* a, const fheram_keys* k);
 // Ram::read_prepare_write (src/ram.rs:196-222, 461-542).  For a sharded RAM the caller runs
 // fheram_ram_rpw_local_device, all-gathers the partials and calls fheram_ram_rpw_finish_device
 // on every rank (the finishing stage is replicated so every rank holds tree[0][0]).
@@ -1788,11 +1940,24 @@ extern "C" int fheram_ram_rpw_finish_device(fheram_ram* r, const int32_t* d_gath
 extern "C" int fheram_ram_read_prepare_write(fheram_ram* r, const fheram_address* addr,
                                              const fheram_keys* k, int64_t* out) {
   if (!out) return fail(FHERAM_ERR_INVALID, "null argument");
-  if (r && r->n_shards != 1) return fail(FHERAM_ERR_INVALID, "sharded RAM: use rpw_local_device / rpw_finish_device");
+  if (r && r->n_shards != 1 && !comm_matches(r->c, r->shard, r->n_shards))
+    return fail(FHERAM_ERR_INVALID, "sharded RAM: call fheram_comm_init first, or use rpw_local_device / rpw_finish_device");
   const int32_t *part = nullptr, *res = nullptr;
   TRY(fheram_ram_rpw_local_device(r, addr, k, &part));
+  if (r->n_shards != 1) {
+    // every rank needs tree[0][0] (Ram::write then runs without communication): all-gather the packed partials and
+    // finish on every rank (bit-identical by construction: integer limbs, every combine executed with the same operands)
+    fheram_ctx* c = r->c;
+    const size_t cnt = (size_t)c->params.word_size * c->ct_stride();
+    TRY(r->xchg.ensure(sizeof(int) * cnt * r->n_shards));
+    NC(ncclAllGather(part, r->xchg.p, cnt, ncclInt32, c->comm, c->stream));
+    part = (const int32_t*)r->xchg.p;
+  }
   TRY(fheram_ram_rpw_finish_device(r, part, addr, k, &res));
-  return download_i64(r->c, res, (size_t)r->c->params.word_size * r->c->ct_stride(), out);
+  TRY(download_i64(r->c, res, (size_t)r->c->params.word_size * r->c->ct_stride(), out));
+  // the inverse address the write that follows needs (src/ram.rs:260-271,278-289) is queued now, behind the
+  // downloaded result: it runs while the host works on the word to write instead of at the head of Ram::write
+  return address_prepare_inv(addr, k);
 }
 
 // CoordinatePrepared::prepare_inv for every coordinate of the address (src/ram.rs:260-271,
@@ -1821,10 +1986,11 @@ static int ggsw_invert_device(fheram_ctx* c, const fheram_keys* k, const int* ra
   }
   return 0;
 }
-static int address_prepare_inv(fheram_address* a, const fheram_keys* k) {
+static int address_prepare_inv(const fheram_address* a, const fheram_keys* k) {
   fheram_ctx* c = a->c;
   const Derived& d = c->d;
   if (a->count != 1) return fail(FHERAM_ERR_INVALID, "write takes a single address");
+  if (a->inv_ready) return 0;
   if (!a->inv_raw) {
     CU(cudaMalloc(&a->inv_raw, sizeof(int) * (size_t)d.n_ggsw * c->ggsw_raw_len()));
     CU(cudaMalloc(&a->inv_prep, sizeof(double2) * (size_t)d.n_ggsw * c->ggsw_prep_len()));
@@ -1837,11 +2003,13 @@ static int address_prepare_inv(fheram_address* a, const fheram_keys* k) {
 
 // Ram::write (src/ram.rs:226-294).  Works on sharded RAMs without communication: the steps that
 // touch tree[0][0] are replicated on every rank, the rest touches only local polynomials.
-extern "C" int fheram_ram_write(fheram_ram* r, const int64_t* w, const fheram_address* addr_c,
+extern "C" int fheram_ram_write(fheram_ram* r, const int64_t* w, const fheram_address* addr,
                                 const fheram_keys* k) {
-  if (!r || !w || !addr_c || !k) return fail(FHERAM_ERR_INVALID, "null argument");
-  fheram_address* addr = const_cast<fheram_address*>(addr_c);
+  if (!r || !addr || !k) return fail(FHERAM_ERR_INVALID, "null argument");
   fheram_ctx* c = r->c;
+  const bool bcast = r->n_shards != 1 && comm_matches(c, r->shard, r->n_shards);
+  // with a communicator the written word is rank 0's, broadcast over NVLink: the other ranks may pass NULL
+  if (!w && !(bcast && r->shard != 0)) return fail(FHERAM_ERR_INVALID, "null argument");
   if (addr->c != c || k->c != c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
   if (!r->state)
     return fail(FHERAM_ERR_NOT_READY, "invalid call to Memory.write: internal state is false -> requires calling Memory.read_prepare_write (src/ram.rs:555-558)");
@@ -1851,7 +2019,15 @@ extern "C" int fheram_ram_write(fheram_ram* r, const int64_t* w, const fheram_ad
   const long L = c->ct_stride();
   const int per = ws * nl;
   TRY(r->wbuf.ensure(sizeof(int) * (size_t)ws * L));
-  TRY(upload_i64(c, w, (size_t)ws * L, (int*)r->wbuf.p));
+  if (!bcast || r->shard == 0) {
+    // staged through a buffer of its own and not waited for: the copy out of pageable memory returns once the
+    // host data is staged, the conversion is ordered on the stream
+    TRY(r->wstage.ensure(sizeof(long long) * (size_t)ws * L));
+    CU(cudaMemcpyAsync(r->wstage.p, w, sizeof(long long) * (size_t)ws * L, cudaMemcpyHostToDevice, c->stream));
+    k_i64_to_i32<<<c->sm_count, 256, 0, c->stream>>>((const long long*)r->wstage.p, (int*)r->wbuf.p, (size_t)ws * L, c->d_err);
+    c->launches++;
+  }
+  if (bcast) NC(ncclBroadcast(r->wbuf.p, r->wbuf.p, (size_t)ws * L, ncclInt32, 0, c->comm, c->stream));
   TRY(r->bufA.ensure(sizeof(int) * (size_t)per * L));
   TRY(r->bufB.ensure(sizeof(int) * (size_t)per * L));
   int* A = (int*)r->bufA.p;
@@ -1888,7 +2064,8 @@ extern "C" int fheram_ram_write(fheram_ram* r, const int64_t* w, const fheram_ad
   // write_last_step (src/ram.rs:634-649): rotate every polynomial back by the first coordinate
   TRY(run_ext_chain(c, per, r->data, nullptr, 0, r->data, addr->inv_prep, d.coord_len[0], 0, 0));
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));
+  // no host synchronisation: the call returns with the work queued on the context stream, like every *_device entry
+  // point; the next call on this RAM is ordered after it, fheram_ctx_synchronize / any download waits for it
   r->state = false;  // src/ram.rs:648
   return 0;
 }

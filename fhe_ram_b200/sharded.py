@@ -1,4 +1,13 @@
-"""Sharded multi-GPU FHE-RAM: one process per GPU, torch.distributed for the plumbing.
+"""Sharded multi-GPU FHE-RAM: one process per GPU.
+
+Two layers:
+  * ShardedRamLib -- the product path: the exchange steps (all-gather of prepared GGSWs, all-to-all of packed
+    partials, all-gather for read_prepare_write, broadcast of the written word) run INSIDE libfheram_cuda.so on its
+    own NCCL communicator (fheram_comm_init); Python only hands the 128-byte communicator id from rank 0 to the
+    other ranks (torch.distributed object broadcast) and calls the same entry points as on one GPU.
+  * ShardedRam -- the same schedule with the exchange done by torch.distributed around an `engine` object
+    (GpuEngine = the *_local_device / *_finish_device halves of the C ABI; tests substitute an oracle-backed engine to
+    exercise the host logic with gloo on CPU).
 
 Partition: rank g keeps the polynomials h == g (mod G) of every sub-RAM.  The packer feeds its
 inputs in bit-reversed order (src/ram.rs:426,512), so the polynomials of one rank form one
@@ -36,7 +45,12 @@ class _DevView:
 
 
 class GpuEngine:
-    """Local / finishing stages through libfheram_cuda.so (include/fheram.h)."""
+    """Local / finishing stages through libfheram_cuda.so (include/fheram.h).
+
+    Stream contract: the library queues its kernels on the context's private stream while torch's collectives order
+    against torch's CURRENT stream, so every method of ShardedRam that touches this engine runs inside
+    `self.stream_ctx()` (the context stream as torch's current stream): partials are complete before NCCL reads
+    them and are not overwritten while it still does."""
 
     def __init__(self, params, rank: int, world: int, cts_full: np.ndarray):
         from . import api
@@ -44,6 +58,10 @@ class GpuEngine:
         self.ram = api.Ram(params, shard=rank, n_shards=world)
         self.ram.load(cts_full)
         self.L = params.word_size() * params.glwe_len()     # int32 limbs per read result / partial
+
+    def stream_ctx(self):
+        import torch
+        return torch.cuda.stream(torch.cuda.ExternalStream(self.params.stream(), device=self.params.device))
 
     def _tensor(self, ptr, n):
         import torch
@@ -93,6 +111,11 @@ class ShardedRam:
         assert world & (world - 1) == 0, "world size must be a power of two"
         self.e, self.rank, self.world = engine, rank, world
 
+    def _ctx(self):
+        """the engine's stream as torch's current stream (GpuEngine); engines without one run as they are"""
+        import contextlib
+        return self.e.stream_ctx() if hasattr(self.e, "stream_ctx") else contextlib.nullcontext()
+
     # ---- batched reads ------------------------------------------------------------------
     def read_batch_local_slice(self, addrs, keys):
         """B = addrs.count independent reads.  Returns this rank's slice of the results:
@@ -100,106 +123,83 @@ class ShardedRam:
         import torch.distributed as dist
         B, G = addrs.count, self.world
         assert B % G == 0, "batch must be a multiple of the world size"
-        part = self.e.read_local(addrs, keys)                  # [B][ws] partials of the local slice
-        if G == 1:
-            return self.e.read_finish(part, B, addrs, 0, keys)
-        recv = self.e.empty(part.numel())                      # [G shards][B/G][ws]
-        dist.all_to_all_single(recv, part)                     # chunk r of `part` = reads of rank r
-        return self.e.read_finish(recv, B // G, addrs, self.rank * (B // G), keys)
+        with self._ctx():
+            part = self.e.read_local(addrs, keys)                  # [B][ws] partials of the local slice
+            if G == 1:
+                return self.e.read_finish(part, B, addrs, 0, keys)
+            recv = self.e.empty(part.numel())                      # [G shards][B/G][ws]
+            dist.all_to_all_single(recv, part)                     # chunk r of `part` = reads of rank r
+            return self.e.read_finish(recv, B // G, addrs, self.rank * (B // G), keys)
 
     def read_batch(self, addrs, keys):
         """all B results on every rank ([B][word_size][limbs] int64 numpy), for tests"""
         import torch.distributed as dist
-        mine = self.read_batch_local_slice(addrs, keys)
-        if self.world == 1:
-            return self.e.to_host(mine)
-        full = self.e.empty(mine.numel() * self.world)
-        dist.all_gather_into_tensor(full, mine.contiguous())
-        return self.e.to_host(full)
+        with self._ctx():
+            mine = self.read_batch_local_slice(addrs, keys)
+            if self.world == 1:
+                return self.e.to_host(mine)
+            full = self.e.empty(mine.numel() * self.world)
+            dist.all_gather_into_tensor(full, mine.contiguous())
+            return self.e.to_host(full)
 
     # ---- read_prepare_write / write -----------------------------------------------------
     def read_prepare_write(self, addr, keys):
         import torch.distributed as dist
-        part = self.e.rpw_local(addr, keys)
-        if self.world > 1:
-            gathered = self.e.empty(part.numel() * self.world)  # [G][1][ws]
-            dist.all_gather_into_tensor(gathered, part.contiguous())
-        else:
-            gathered = part
-        return self.e.to_host(self.e.rpw_finish(gathered, addr, keys))
+        with self._ctx():
+            part = self.e.rpw_local(addr, keys)
+            if self.world > 1:
+                gathered = self.e.empty(part.numel() * self.world)  # [G][1][ws]
+                dist.all_gather_into_tensor(gathered, part.contiguous())
+            else:
+                gathered = part
+            return self.e.to_host(self.e.rpw_finish(gathered, addr, keys))
 
     def write(self, w, addr, keys):
         """Ram::write (src/ram.rs:226-294): no communication (see module docstring)."""
         self.e.write(w, addr, keys)
 
-    # ---- bench helpers ------------------------------------------------------------------
-    def bench_closures(self, api, addr_limbs, keys, B, out_host):
-        """(run_resident, run_e2e) closures for bench.py"""
-        params = self.e.params
-        resident = api.Address.from_limbs(params, addr_limbs, B)
-        resident.device()
 
-        def run_resident():
-            return self.read_batch_local_slice(resident, keys)
+class ShardedRamLib:
+    """Ram (src/ram.rs:25-29) sharded over the ranks of the default process group, every exchange step inside the
+    library (include/fheram.h, fheram_comm_*).  The calls are the single-GPU ones; what differs is what they mean on
+    a sharded RAM (see the header): batches are split over the ranks, read_prepare_write returns the same result on
+    every rank, write takes rank 0's word."""
 
-        import torch
-        import torch.distributed as dist
-        G, rank = self.world, self.rank
-        per = params.n_ggsw() * params.ggsw_len()          # int32 limbs per address on the device
+    def __init__(self, params, rank: int, world: int, cts_full: np.ndarray | None = None):
+        from . import api
+        assert world & (world - 1) == 0, "world size must be a power of two"
+        self.api, self.params, self.rank, self.world = api, params, rank, world
+        if world > 1:
+            import torch.distributed as dist
+            box = [api.Parameters.comm_unique_id().tobytes() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            params.comm_init(world, rank, np.frombuffer(box[0], dtype=np.uint8))
+        self.ram = api.Ram(params, shard=rank, n_shards=world)
+        if cts_full is not None:
+            self.ram.load(cts_full)
 
-        # host-buffer path, pipelined in chunks of reads per rank: every rank uploads only its own addresses over
-        # PCIe on a copy stream (the others arrive over NVLink with one all-gather per chunk), so the upload of
-        # chunk k+1 overlaps prepare / read / exchange / finish of chunk k.  The first chunks are small (their
-        # upload overlaps nothing), then the size doubles up to `chunk`.
-        cnt = B // G
-        chunk = max(1, min(64, max(16, cnt // 4), cnt))
-        sched = []                                  # (first read of the rank's slice, reads) per chunk
-        b, sz = 0, min(8, chunk)
-        while b < cnt:
-            nb = min(sz, cnt - b)
-            sched.append((b, nb))
-            b += nb
-            sz = min(2 * sz, chunk)
-        # two address sets per chunk size (double buffering), each sized exactly: G * nb addresses
-        sets = {}
-        for _, nb in sched:
-            if nb not in sets:
-                sets[nb] = [api.Address.device_alloc(params, nb * G) for _ in range(2)]
-        use = []                                    # address set of every chunk (alternating within a size)
-        seen = {}
-        for _, nb in sched:
-            k = seen.get(nb, 0)
-            use.append(sets[nb][k & 1])
-            seen[nb] = k + 1
+    def read_batch(self, addrs, keys) -> np.ndarray:
+        """addrs = the whole batch (the same on every rank); returns this rank's slice of the results"""
+        return self.ram.read_batch(addrs, keys)
 
-        def run_e2e():
-            def issue_upload(ci):
-                b0, nb = sched[ci]
-                # chunk layout on the device: [G ranks][nb] so that one all-gather completes it
-                use[ci].upload_slice_async(addr_limbs[rank * cnt + b0:rank * cnt + b0 + nb], rank * nb, nb)
+    def read_batch_device(self, addrs, keys) -> int:
+        return self.ram.read_batch_device(addrs, keys)
 
-            issue_upload(0)
-            for ci, (b0, nb) in enumerate(sched):
-                if ci + 1 < len(sched):
-                    issue_upload(ci + 1)
-                a = use[ci]
-                a.wait_upload()
-                if G > 1:
-                    full = torch.as_tensor(_DevView(a.raw_ptr(), G * nb * per), device=f"cuda:{params.device}")
-                    dist.all_gather_into_tensor(full, full[rank * nb * per:(rank + 1) * nb * per])
-                a.prepare()
-                # the chunk holds G*nb addresses, [r][j] = read (r*cnt + b0 + j): this rank finishes the nb reads
-                # of its own row
-                part = self.e.read_local(a, keys)                      # [G*nb][ws] local partials
-                if G > 1:
-                    recv = self.e.empty(part.numel())
-                    dist.all_to_all_single(recv, part)
-                else:
-                    recv = part
-                mine = self.e.read_finish(recv, nb, a, rank * nb, keys)
-                a.release()
-                api._check(api.lib().fheram_download_glwe(params.module(), C.c_void_p(mine.data_ptr()),
-                                                          nb * params.word_size(), api._p(out_host[b0:b0 + nb])))
-            return out_host
+    def read_batch_host(self, my_addr_limbs, n, keys, out=None, i32=False):
+        """my_addr_limbs = THIS rank's n addresses (host limbs); returns this rank's n results"""
+        fn = self.ram.read_batch_host_i32 if i32 else self.ram.read_batch_host
+        return fn(my_addr_limbs, n, keys, out)
 
-        return run_resident, run_e2e
+    def read_prepare_write(self, addr, keys) -> np.ndarray:
+        return self.ram.read_prepare_write(addr, keys)
+
+    def write(self, w, addr, keys) -> None:
+        self.ram.write(w, addr, keys)
+
+    def store(self) -> np.ndarray:
+        return self.ram.store()
+
+    def close(self):
+        self.ram.close()
+        if self.world > 1:
+            self.params.comm_destroy()

@@ -165,6 +165,10 @@ int fheram_ram_read_batch(fheram_ram *r, const fheram_address *addr, const fhera
  * reads of chunk k). */
 int fheram_ram_read_batch_host(fheram_ram *r, const int64_t *ggsw, int n, const fheram_keys *k,
                                int64_t *out);
+/* compact host format: the same limbs as int32 (normalised base-2^17 digits need 17 bits; Poulpy's containers hold
+ * them as int64): half the bytes over PCIe in both directions and no conversion pass.  Not range checked. */
+int fheram_ram_read_batch_host_i32(fheram_ram *r, const int32_t *ggsw, int n, const fheram_keys *k,
+                                   int32_t *out);
 /* device-resident variant: result left in the RAM's result arena (int32 device limbs,
  * [n][word_size][limb][col][N]); returns the device pointer.  No host copies. */
 int fheram_ram_read_batch_device(fheram_ram *r, const fheram_address *addr, const fheram_keys *k,
@@ -172,7 +176,26 @@ int fheram_ram_read_batch_device(fheram_ram *r, const fheram_address *addr, cons
 /* convert + copy a device result arena to host int64 limbs */
 int fheram_download_glwe(fheram_ctx *ctx, const int32_t *d_in, int n_glwe, int64_t *out);
 
-/* ---- sharded multi-GPU reads: this RAM holds only the polynomials
+/* ---- multi-GPU (the reference's caller makes ONE call per read / read_prepare_write / write,
+ * src/ram.rs:172-176,196-200,226-231, and so does the caller here): one context per GPU and rank, an NCCL
+ * communicator over NVLink inside the library.  Rank 0 draws the id, the host program hands the 128 bytes to the
+ * other ranks (MPI_Bcast, a TCP store, a file), every rank calls fheram_comm_init on its context and creates its RAM
+ * with fheram_ram_create_sharded(ctx, rank, n_ranks).  From then on, on such a RAM:
+ *   fheram_ram_read_batch_host[_i32]   every rank passes ITS n addresses and receives ITS n results (global batch =
+ *                                      concatenation over ranks); prepared GGSWs all-gathered, partials all-to-all
+ *   fheram_ram_read_batch[_device]     addr = the WHOLE batch on every rank; rank q receives reads [qB/G, (q+1)B/G)
+ *   fheram_ram_read_prepare_write      all-gather of the packed partials, result and tree[0][0] on every rank
+ *   fheram_ram_write                   the word of rank 0 is broadcast (other ranks may pass NULL); every rank
+ *                                      updates its own polynomials
+ * Only integer limbs cross the links (never a floating-point reduction), so results are bit-identical to one GPU. */
+int fheram_comm_unique_id(uint8_t id[128]);
+int fheram_comm_init(fheram_ctx *ctx, int n_ranks, int rank, const uint8_t id[128]);
+int fheram_comm_destroy(fheram_ctx *ctx);
+int fheram_comm_n_ranks(const fheram_ctx *ctx);
+int fheram_comm_rank(const fheram_ctx *ctx);
+
+/* ---- the halves of the sharded calls, for callers that run the exchange themselves (tests emulate the ranks on one
+ * GPU with them; fheram_comm_init is not needed): this RAM holds only the polynomials
  * h == shard (mod n_shards) of every sub-RAM.  Local stage: rotate + pack the local slice;
  * partial results ([n][word_size] GLWE, int32 device limbs) are exchanged by the caller
  * (NCCL all-gather) and finished with fheram_ram_read_finish_sharded on every rank. ---- */

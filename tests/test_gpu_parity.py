@@ -228,6 +228,9 @@ def test_host_buffer_batch_pipeline(scenario, gpu_keys):
     for b in (0, 1, 31, 32, 63, 64, 69):
         assert np.array_equal(got[b], ram.read(addrs[b], keys)), b
         s.check_decrypt(got[b], idxs[b])
+    # compact host format (int32 limbs in and out): the same limbs
+    got32 = ram.read_batch_host_i32(limbs.astype(np.int32), len(idxs), keys)
+    assert got32.dtype == np.int32 and np.array_equal(got32.astype(np.int64), got)
     bad = limbs.copy()
     bad[3, 5] = 1 << 40
     with pytest.raises(fr.FheRamError) as e:
