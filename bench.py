@@ -256,12 +256,16 @@ def main():
     keys = fr.EvaluationKeysPrepared.alloc(params).prepare(evk)
     data = fr.Source(5).fill_bytes(max_addr * ws)
     import ctypes as C
-    cts = np.zeros(ws * params.n_glwe() * params.glwe_len(), dtype=np.int64)
-    xa, xe = fr.Source(11), fr.Source(12)
-    t0 = time.perf_counter()
-    api._check(api.lib().fheram_encrypt_ram(C.byref(params.c), data.ctypes.data_as(api._PU8), api._p(sk.data),
-                                            xa.h, xe.h, api._p(cts)))
-    t_ram_cpu = time.perf_counter() - t0
+    cts, t_ram_cpu = None, None
+    if world == 1:
+        # the client side on the CPU (also the RAM of the cpu_baseline); N > 1: every rank encrypts its own shard on
+        # its GPU (Ram::encrypt_sk on the device: the same limbs from the same Sources, tests/test_gpu_encrypt.py)
+        cts = np.zeros(ws * params.n_glwe() * params.glwe_len(), dtype=np.int64)
+        xa, xe = fr.Source(11), fr.Source(12)
+        t0 = time.perf_counter()
+        api._check(api.lib().fheram_encrypt_ram(C.byref(params.c), data.ctypes.data_as(api._PU8), api._p(sk.data),
+                                                xa.h, xe.h, api._p(cts)))
+        t_ram_cpu = time.perf_counter() - t0
     B = args.batch
     assert B % world == 0, "--batch must be a multiple of the number of GPUs"
     mine = B // world                                   # reads this rank finishes: [first, first + mine)
@@ -290,7 +294,8 @@ def main():
 
     if world > 1:
         from fhe_ram_b200.sharded import ShardedRamLib
-        ram = ShardedRamLib(params, rank, world, cts)
+        ram = ShardedRamLib(params, rank, world)
+        ram.ram.encrypt_sk_gpu(data, sk, fr.Source(11), fr.Source(12))
     else:
         ram = fr.Ram.new(params)
         ram.load(cts)
@@ -361,7 +366,7 @@ def main():
     parity = None
     if world > 1:
         single = fr.Ram.new(params)
-        single.load(cts)
+        single.encrypt_sk_gpu(data, sk, fr.Source(11), fr.Source(12))
         own = fr.Address.from_limbs(params, my_limbs64, mine)
         want = single.read_batch(own, keys)
         same = bool(np.array_equal(want, res))

@@ -134,6 +134,13 @@ using GLWE = std::vector<int64_t>;
 class Ram {  // src/ram.rs:25-29
  public:
   explicit Ram(Parameters& p) : p_(p) { check(fheram_ram_create(p.module(), &h_)); }  // Ram::new()
+  // multi-GPU (one process per GPU): rank `rank` of `n_ranks`; id = the 128 bytes of Ram::comm_unique_id() on rank 0,
+  // handed to the other ranks by the host program.  read / read_prepare_write / write keep their signatures.
+  Ram(Parameters& p, int n_ranks, int rank, const uint8_t (&id)[128]) : p_(p) {
+    check(fheram_comm_init(p.module(), n_ranks, rank, id));
+    check(fheram_ram_create_sharded(p.module(), rank, n_ranks, &h_));
+  }
+  static void comm_unique_id(uint8_t (&id)[128]) { check(fheram_comm_unique_id(id)); }
   ~Ram() { if (h_) fheram_ram_destroy(h_); }
   void encrypt_sk(const std::vector<uint8_t>& data, const GLWESecret& sk, Source& xa, Source& xe) {  // :129-167
     if (data.size() % p_.word_size() != 0) throw Panic(-1, "invalid data: data.len()%ram_chunks != 0");

@@ -1150,6 +1150,8 @@ struct fheram_ram {
   DevBuf result;             // [B][word_size] results
   DevBuf wbuf;               // uploaded write words
   DevBuf wstage;             // their int64 staging
+  void* wpin = nullptr;      // pinned host copy of the words of the write in flight
+  cudaEvent_t wcopied = nullptr;
   DevBuf all;                // results of a chunked batched read
   DevBuf xchg;               // sharded: partials received from the other ranks, [n_shards][reads][word_size]
   DevBuf part_all;           // sharded, device-resident batch: partials of every read before the exchange
@@ -1195,6 +1197,7 @@ extern "C" int fheram_ram_destroy(fheram_ram* r) {
   if (!r) return 0;
   cudaSetDevice(r->c->device);
   cudaFree(r->data); cudaFree(r->tree); cudaFree(r->feed_map);
+  if (r->wpin) { cudaStreamSynchronize(r->c->stream); cudaFreeHost(r->wpin); cudaEventDestroy(r->wcopied); }
   r->bufA.release(); r->bufB.release(); r->partial.release(); r->result.release(); r->wbuf.release(); r->wstage.release(); r->all.release(); r->xchg.release(); r->part_all.release();
   for (auto& s : r->pipe.sets) {
     cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
@@ -2023,7 +2026,17 @@ extern "C" int fheram_ram_write(fheram_ram* r, const int64_t* w, const fheram_ad
     // staged through a buffer of its own and not waited for: the copy out of pageable memory returns once the
     // host data is staged, the conversion is ordered on the stream
     TRY(r->wstage.ensure(sizeof(long long) * (size_t)ws * L));
-    CU(cudaMemcpyAsync(r->wstage.p, w, sizeof(long long) * (size_t)ws * L, cudaMemcpyHostToDevice, c->stream));
+    // through a pinned buffer of the RAM handle: the caller's words may be freed as soon as the call returns
+    const size_t wbytes = sizeof(long long) * (size_t)ws * L;
+    if (!r->wpin) {
+      CU(cudaMallocHost(&r->wpin, wbytes));
+      CU(cudaEventCreateWithFlags(&r->wcopied, cudaEventDisableTiming));
+    } else {
+      CU(cudaEventSynchronize(r->wcopied));  // the previous write's copy out of the buffer (long done)
+    }
+    memcpy(r->wpin, w, wbytes);
+    CU(cudaMemcpyAsync(r->wstage.p, r->wpin, wbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(r->wcopied, c->stream));
     k_i64_to_i32<<<c->sm_count, 256, 0, c->stream>>>((const long long*)r->wstage.p, (int*)r->wbuf.p, (size_t)ws * L, c->d_err);
     c->launches++;
   }

@@ -43,6 +43,18 @@ extern "C" {
     pub fn fheram_ram_read_batch(r: *mut fheram_ram, a: *const fheram_address, k: *const fheram_keys, out: *mut i64) -> c_int;
     pub fn fheram_ram_read_batch_host(r: *mut fheram_ram, ggsw_host: *const i64, n: c_int, k: *const fheram_keys,
                                       out_host: *mut i64) -> c_int;
+    // compact host format (int32 limbs in and out)
+    pub fn fheram_ram_read_batch_host_i32(r: *mut fheram_ram, ggsw_host: *const i32, n: c_int, k: *const fheram_keys,
+                                          out_host: *mut i32) -> c_int;
+    // multi-GPU: NCCL communicator inside the library (one rank per context); on a RAM from
+    // fheram_ram_create_sharded(ctx, rank, n_ranks) the read / read_prepare_write / write calls above then do their own
+    // exchange steps (see include/fheram.h)
+    pub fn fheram_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn fheram_comm_init(c: *mut fheram_ctx, n_ranks: c_int, rank: c_int, id: *const u8) -> c_int;
+    pub fn fheram_comm_destroy(c: *mut fheram_ctx) -> c_int;
+    pub fn fheram_comm_n_ranks(c: *const fheram_ctx) -> c_int;
+    pub fn fheram_comm_rank(c: *const fheram_ctx) -> c_int;
+    pub fn fheram_ram_create_sharded(c: *mut fheram_ctx, shard: c_int, n_shards: c_int, out: *mut *mut fheram_ram) -> c_int;
     // multi-GPU building blocks (one process per GPU): each rank uploads 1/G of a batch and all-gathers the rest
     pub fn fheram_address_alloc(c: *mut fheram_ctx, n: c_int, out: *mut *mut fheram_address) -> c_int;
     pub fn fheram_address_upload_slice_async(a: *mut fheram_address, ggsw: *const i64, first: c_int, count: c_int) -> c_int;

@@ -29,6 +29,22 @@ impl Parameters {
         unsafe { fheram_params_default(&mut c) };
         Parameters { c, ctx: std::ptr::null_mut() }
     }
+    /// README.md:17-34 parameter set (MAX_ADDR = 2^18, K_PT = 9): BASELINE.json's workload
+    pub fn readme() -> Self {
+        let mut c = unsafe { std::mem::zeroed() };
+        unsafe { fheram_params_readme(&mut c) };
+        Parameters { c, ctx: std::ptr::null_mut() }
+    }
+    /// the runtime overrides of src/ram.rs:72-87 (word_size, decomp_n, max_addr) on top of `new()`
+    pub fn with_ram_params(word_size: usize, decomp_n: Vec<u8>, max_addr: usize) -> Self {
+        let mut p = Self::new();
+        assert!(decomp_n.len() <= 8, "at most 8 digits per coordinate");
+        p.c.word_size = word_size as i32;
+        p.c.max_addr = max_addr as u64;
+        p.c.n_decomp = decomp_n.len() as i32;
+        for (i, d) in decomp_n.iter().enumerate() { p.c.decomp_n[i] = *d as i32; }
+        p
+    }
     pub fn max_addr(&self) -> usize { self.c.max_addr as usize }
     pub fn word_size(&self) -> usize { self.c.word_size as usize }
     pub fn k_glwe_pt(&self) -> u32 { self.c.k_pt as u32 }
@@ -114,11 +130,32 @@ pub type GLWE = Vec<i64>;
 /// src/ram.rs:25-29
 pub struct Ram { pub params: Parameters, h: *mut fheram_ram }
 impl Ram {
-    pub fn new() -> Self {
-        let mut params = Parameters::new();
+    /// src/ram.rs:59-69
+    pub fn new() -> Self { Self::from_params(Parameters::new()) }
+    /// src/ram.rs:72-87
+    pub fn new_from_ram_params(word_size: usize, decomp_n: Vec<u8>, max_addr: usize) -> Self {
+        Self::from_params(Parameters::with_ram_params(word_size, decomp_n, max_addr))
+    }
+    /// README.md:116-155 parameter set
+    pub fn new_readme() -> Self { Self::from_params(Parameters::readme()) }
+    pub fn from_params(mut params: Parameters) -> Self {
         let mut h = std::ptr::null_mut();
         check(unsafe { fheram_ram_create(params.module(), &mut h) });
         Ram { params, h }
+    }
+    /// multi-GPU: rank `rank` of `n_ranks` (one process per GPU).  `id` = the 128 bytes rank 0 got from
+    /// `Ram::comm_unique_id()` and handed to the other ranks (MPI, a TCP store, ...).  read / read_prepare_write /
+    /// write keep their signatures; batched reads split the batch over the ranks (include/fheram.h).
+    pub fn new_sharded(mut params: Parameters, n_ranks: usize, rank: usize, id: &[u8; 128]) -> Self {
+        check(unsafe { fheram_comm_init(params.module(), n_ranks as i32, rank as i32, id.as_ptr()) });
+        let mut h = std::ptr::null_mut();
+        check(unsafe { fheram_ram_create_sharded(params.module(), rank as i32, n_ranks as i32, &mut h) });
+        Ram { params, h }
+    }
+    pub fn comm_unique_id() -> [u8; 128] {
+        let mut id = [0u8; 128];
+        check(unsafe { fheram_comm_unique_id(id.as_mut_ptr()) });
+        id
     }
     /// src/ram.rs:129-167
     pub fn encrypt_sk(&mut self, data: &[u8], sk: &GLWESecret, xa: &mut Source, xe: &mut Source) {
