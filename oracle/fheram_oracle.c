@@ -357,28 +357,89 @@ static void tf_init(orc_ctx *c) {
 }
 static void tf_free(orc_ctx *c) { free(c->tw_re); free(c->tw_im); }
 /* layout: out[0..m) real parts, out[m..2m) imaginary parts, frequency order bit-reversed
- * (private to the backend) */
+ * (private to the backend).
+ * Written so that gcc vectorises it (AVX2 / AVX-512 clones picked at load time): stages are fused in pairs
+ * (radix 4: half the passes over the 32 KiB of data), the last two stages (distance 2 and 1) work on blocks
+ * of four, and the int64 <-> double conversions use the 2^52 + 2^51 trick instead of cvtsi2sd / llrint
+ * (exact for |x| < 2^51: inputs are limbs, outputs are < 2^47; same round-to-nearest-even). */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(ORC_NO_CLONES)
+#define ORC_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define ORC_CLONES
+#endif
+#define ORC_MAGIC 6755399441055744.0 /* 2^52 + 2^51 */
+static inline double i64_to_f64(i64 v) {
+  union { double d; i64 i; } u;
+  u.i = v + 0x4338000000000000LL;
+  return u.d - ORC_MAGIC;
+}
+static inline i64 f64_round_i64(double v) {
+  union { double d; i64 i; } u;
+  u.d = v + ORC_MAGIC;
+  return u.i - 0x4338000000000000LL;
+}
+/* forward butterfly pair (x, y) <- (x + w y, x - w y) on arrays of length t */
+static inline void fwd_bf(double *xr, double *xi, double *yr, double *yi, double wr, double wi, int t) {
+  for (int j = 0; j < t; j++) {
+    double vr = yr[j] * wr - yi[j] * wi, vi = yr[j] * wi + yi[j] * wr;
+    double ur = xr[j], ui = xi[j];
+    xr[j] = ur + vr; xi[j] = ui + vi;
+    yr[j] = ur - vr; yi[j] = ui - vi;
+  }
+}
+ORC_CLONES
 static void tf_forward(const orc_ctx *c, const i64 *a, tfe *out, int mont) {
   (void)mont;
   const int m = c->n / 2;
   double *re = out, *im = out + m;
-  for (int i = 0; i < m; i++) { re[i] = (double)a[i]; im[i] = (double)a[i + m]; }
-  int t = m;
-  for (int s = 1; s < m; s <<= 1) {
-    t >>= 1;
+  for (int i = 0; i < m; i++) { re[i] = i64_to_f64(a[i]); im[i] = i64_to_f64(a[i + m]); }
+  int t = m, s = 1;
+  /* fused pairs of stages (s, 2s) while the second stage still has distance >= 4 */
+  for (; (t >> 2) >= 4; s <<= 2) {
+    const int q = t >> 2; /* distance of the second stage; the block of 4q elements splits into quarters */
     for (int b = 0; b < s; b++) {
-      const double wr = c->tw_re[s + b], wi = c->tw_im[s + b];
-      double *xr = re + 2 * b * t, *xi = im + 2 * b * t, *yr = xr + t, *yi = xi + t;
-      for (int j = 0; j < t; j++) {
-        double vr = yr[j] * wr - yi[j] * wi, vi = yr[j] * wi + yi[j] * wr;
-        double ur = xr[j], ui = xi[j];
-        xr[j] = ur + vr; xi[j] = ui + vi;
-        yr[j] = ur - vr; yi[j] = ui - vi;
+      const double w1r = c->tw_re[s + b], w1i = c->tw_im[s + b];
+      const double w2r = c->tw_re[2 * s + 2 * b], w2i = c->tw_im[2 * s + 2 * b];
+      const double w3r = c->tw_re[2 * s + 2 * b + 1], w3i = c->tw_im[2 * s + 2 * b + 1];
+      double *r0 = re + (size_t)b * t, *i0 = im + (size_t)b * t;
+      double *r1 = r0 + q, *i1 = i0 + q, *r2 = r0 + 2 * q, *i2 = i0 + 2 * q, *r3 = r0 + 3 * q, *i3 = i0 + 3 * q;
+      for (int j = 0; j < q; j++) {
+        /* stage s: (0,2) and (1,3) with w1 */
+        double ar = r2[j] * w1r - i2[j] * w1i, ai = r2[j] * w1i + i2[j] * w1r;
+        double br = r3[j] * w1r - i3[j] * w1i, bi = r3[j] * w1i + i3[j] * w1r;
+        double x0r = r0[j] + ar, x0i = i0[j] + ai, x2r = r0[j] - ar, x2i = i0[j] - ai;
+        double x1r = r1[j] + br, x1i = i1[j] + bi, x3r = r1[j] - br, x3i = i1[j] - bi;
+        /* stage 2s: (0,1) with w2, (2,3) with w3 */
+        double cr = x1r * w2r - x1i * w2i, ci = x1r * w2i + x1i * w2r;
+        double dr = x3r * w3r - x3i * w3i, di = x3r * w3i + x3i * w3r;
+        r0[j] = x0r + cr; i0[j] = x0i + ci; r1[j] = x0r - cr; i1[j] = x0i - ci;
+        r2[j] = x2r + dr; i2[j] = x2i + di; r3[j] = x2r - dr; i3[j] = x2i - di;
+      }
+    }
+    t = q;
+  }
+  /* remaining single stages */
+  for (; s < m; s <<= 1) {
+    t >>= 1;
+    if (t >= 4) {
+      for (int b = 0; b < s; b++)
+        fwd_bf(re + 2 * b * t, im + 2 * b * t, re + 2 * b * t + t, im + 2 * b * t + t, c->tw_re[s + b], c->tw_im[s + b], t);
+    } else {
+      for (int b = 0; b < s; b++) {
+        const double wr = c->tw_re[s + b], wi = c->tw_im[s + b];
+        double *xr = re + 2 * b * t, *xi = im + 2 * b * t;
+        for (int j = 0; j < t; j++) {
+          double vr = xr[t + j] * wr - xi[t + j] * wi, vi = xr[t + j] * wi + xi[t + j] * wr;
+          double ur = xr[j], ui = xi[j];
+          xr[j] = ur + vr; xi[j] = ui + vi;
+          xr[t + j] = ur - vr; xi[t + j] = ui - vi;
+        }
       }
     }
   }
 }
 static void tf_zero(const orc_ctx *c, tfe *acc) { memset(acc, 0, sizeof(tfe) * c->n); }
+ORC_CLONES
 static void tf_mac(const orc_ctx *c, tfe *acc, const tfe *a, const tfe *b) {
   const int m = c->n / 2;
   for (int i = 0; i < m; i++) {
@@ -387,27 +448,64 @@ static void tf_mac(const orc_ctx *c, tfe *acc, const tfe *a, const tfe *b) {
     acc[i + m] += ar * bi + ai * br;
   }
 }
+ORC_CLONES
 static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
   const int m = c->n / 2;
   double *re = a, *im = a + m;
-  int t = 1;
-  for (int s = m >> 1; s >= 1; s >>= 1) {
+  int t = 1, s = m >> 1;
+  /* single stages while the distance is below 4 */
+  for (; s >= 1 && t < 4; s >>= 1) {
     for (int b = 0; b < s; b++) {
       const double wr = c->tw_re[s + b], wi = -c->tw_im[s + b];
-      double *xr = re + 2 * b * t, *xi = im + 2 * b * t, *yr = xr + t, *yi = xi + t;
+      double *xr = re + 2 * b * t, *xi = im + 2 * b * t;
       for (int j = 0; j < t; j++) {
-        double ur = xr[j], ui = xi[j], vr = yr[j], vi = yi[j];
+        double ur = xr[j], ui = xi[j], vr = xr[t + j], vi = xi[t + j];
         xr[j] = ur + vr; xi[j] = ui + vi;
         double dr = ur - vr, di = ui - vi;
-        yr[j] = dr * wr - di * wi; yi[j] = dr * wi + di * wr;
+        xr[t + j] = dr * wr - di * wi; xi[t + j] = dr * wi + di * wr;
       }
     }
     t <<= 1;
   }
+  /* fused pairs of stages (s, s / 2): distance t then 2t */
+  for (; s >= 2; s >>= 2) {
+    const int h = s >> 1; /* blocks of the second stage */
+    for (int b = 0; b < h; b++) {
+      const double w2r = c->tw_re[s + 2 * b], w2i = -c->tw_im[s + 2 * b];
+      const double w3r = c->tw_re[s + 2 * b + 1], w3i = -c->tw_im[s + 2 * b + 1];
+      const double w1r = c->tw_re[h + b], w1i = -c->tw_im[h + b];
+      double *r0 = re + (size_t)b * 4 * t, *i0 = im + (size_t)b * 4 * t;
+      double *r1 = r0 + t, *i1 = i0 + t, *r2 = r0 + 2 * t, *i2 = i0 + 2 * t, *r3 = r0 + 3 * t, *i3 = i0 + 3 * t;
+      for (int j = 0; j < t; j++) {
+        /* stage s: (0,1) with w2, (2,3) with w3 */
+        double x0r = r0[j] + r1[j], x0i = i0[j] + i1[j], d0r = r0[j] - r1[j], d0i = i0[j] - i1[j];
+        double x2r = r2[j] + r3[j], x2i = i2[j] + i3[j], d1r = r2[j] - r3[j], d1i = i2[j] - i3[j];
+        double x1r = d0r * w2r - d0i * w2i, x1i = d0r * w2i + d0i * w2r;
+        double x3r = d1r * w3r - d1i * w3i, x3i = d1r * w3i + d1i * w3r;
+        /* stage s / 2: (0,2) and (1,3) with w1 */
+        r0[j] = x0r + x2r; i0[j] = x0i + x2i;
+        r1[j] = x1r + x3r; i1[j] = x1i + x3i;
+        double e0r = x0r - x2r, e0i = x0i - x2i, e1r = x1r - x3r, e1i = x1i - x3i;
+        r2[j] = e0r * w1r - e0i * w1i; i2[j] = e0r * w1i + e0i * w1r;
+        r3[j] = e1r * w1r - e1i * w1i; i3[j] = e1r * w1i + e1i * w1r;
+      }
+    }
+    t <<= 2;
+  }
+  if (s == 1) { /* one stage left */
+    const double wr = c->tw_re[1], wi = -c->tw_im[1];
+    double *xr = re, *xi = im, *yr = re + t, *yi = im + t;
+    for (int j = 0; j < t; j++) {
+      double ur = xr[j], ui = xi[j], vr = yr[j], vi = yi[j];
+      xr[j] = ur + vr; xi[j] = ui + vi;
+      double dr = ur - vr, di = ui - vi;
+      yr[j] = dr * wr - di * wi; yi[j] = dr * wi + di * wr;
+    }
+  }
   const double sc = 1.0 / (double)m;
   for (int i = 0; i < m; i++) {
-    out[i] = (i64)llrint(re[i] * sc);
-    out[i + m] = (i64)llrint(im[i] * sc);
+    out[i] = f64_round_i64(re[i] * sc);
+    out[i + m] = f64_round_i64(im[i] * sc);
   }
 }
 #endif
