@@ -163,8 +163,8 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads in the cpu_baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--host-format", default="i32", choices=["i32", "i64"],
-                    help="host limb format of the e2e call: int32 (compact) or int64 (Poulpy's containers)")
+    ap.add_argument("--host-format", default="p17", choices=["p17", "i32", "i64"],
+                    help="host limb format of the e2e call: packed 17-bit fields, int32, or int64 (Poulpy's containers)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -276,8 +276,9 @@ def main():
     t0 = time.perf_counter()
     my_limbs64 = make_addresses(fr, params, sk, idxs[first:first + mine], threads, first)
     t_addr = time.perf_counter() - t0
-    i32 = args.host_format == "i32"
-    my_limbs = my_limbs64.astype(np.int32) if i32 else my_limbs64
+    fmt = args.host_format
+    i32 = fmt != "i64"                                  # results come back as int32 limbs unless the host format is int64
+    my_limbs = {"p17": lambda: api.pack17(my_limbs64), "i32": lambda: my_limbs64.astype(np.int32), "i64": lambda: my_limbs64}[fmt]()
     api.host_register(my_limbs)
     stream = torch.cuda.ExternalStream(params.stream(), device=device)
     L = params.glwe_len()
@@ -306,8 +307,8 @@ def main():
     def run_e2e():
         # this rank's host address limbs -> device, prepare, read (all exchange steps), results back on the host
         if world > 1:
-            return ram.read_batch_host(my_limbs, mine, keys, out_host, i32=i32)
-        return (ram.read_batch_host_i32 if i32 else ram.read_batch_host)(my_limbs, mine, keys, out_host)
+            return ram.read_batch_host(my_limbs, mine, keys, out_host, fmt=fmt)
+        return {"p17": ram.read_batch_host_p17, "i32": ram.read_batch_host_i32, "i64": ram.read_batch_host}[fmt](my_limbs, mine, keys, out_host)
 
     def check(out):
         """decrypt a sample of this rank's results (examples/fhe-ram.rs:104-115)"""
@@ -390,15 +391,16 @@ def main():
         out = run_e2e()
         check(out)
         assert np.array_equal(out.astype(np.int64), res), "host-buffer path != device-resident path"
-        eb = 4 if i32 else 8
+        h2d = int(my_limbs.nbytes) * world
         e2e = {"value": B / (ms_e2e / args.steps * 1e-3), "unit": "reads/s",
-               "h2d_bytes_per_step": int(B * per * eb), "d2h_bytes_per_step": int(B * ws * L * eb),
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(out_host.nbytes) * world,
                "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall / args.steps,
-               "host_format": args.host_format + (" limbs (compact format of the C ABI: fheram_ram_read_batch_host_i32)" if i32
-                                                   else " limbs (Poulpy's VecZnx containers)"),
-               "h2d_gb_per_s_per_gpu": B * per * eb / world / (ms_e2e / args.steps * 1e-3) / 1e9,
-               "call": "fheram_ram_read_batch_host" + ("_i32" if i32 else "") + ": every rank passes its own batch / n_gpus addresses"}
-        if world == 1 and i32:   # the int64 host format once, for the record (same call, twice the PCIe bytes)
+               "host_format": {"p17": "addresses as packed 17-bit fields (fheram_pack17), results as int32 limbs",
+                               "i32": "int32 limbs in and out", "i64": "int64 limbs (Poulpy's VecZnx containers) in and out"}[fmt],
+               "h2d_gb_per_s_per_gpu": h2d / world / (ms_e2e / args.steps * 1e-3) / 1e9,
+               "call": {"p17": "fheram_ram_read_batch_host_p17", "i32": "fheram_ram_read_batch_host_i32",
+                        "i64": "fheram_ram_read_batch_host"}[fmt] + ": every rank passes its own batch / n_gpus addresses"}
+        if world == 1 and fmt != "i64":   # the other host formats once, for the record (same pipeline, more PCIe bytes)
             l64 = my_limbs64
             api.host_register(l64)
             o64 = np.zeros((mine, ws, L), dtype=np.int64)

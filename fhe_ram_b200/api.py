@@ -104,6 +104,9 @@ SIGNATURES = {
     "fheram_ram_read_batch": (C.c_int, [_V, _V, _V, _P64]),
     "fheram_ram_read_batch_host": (C.c_int, [_V, _P64, C.c_int, _V, _P64]),
     "fheram_ram_read_batch_host_i32": (C.c_int, [_V, C.POINTER(C.c_int32), C.c_int, _V, C.POINTER(C.c_int32)]),
+    "fheram_ram_read_batch_host_p17": (C.c_int, [_V, C.POINTER(C.c_uint32), C.c_int, _V, C.POINTER(C.c_int32)]),
+    "fheram_pack17": (C.c_int, [_P64, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "fheram_unpack17": (C.c_int, [C.POINTER(C.c_uint32), C.c_size_t, _P64]),
     "fheram_ram_read_batch_device": (C.c_int, [_V, _V, _V, _PV]),
     "fheram_comm_unique_id": (C.c_int, [_PU8]),
     "fheram_comm_init": (C.c_int, [_V, C.c_int, C.c_int, _PU8]),
@@ -302,6 +305,21 @@ class Parameters:
         if self._ctx is not None:
             lib().fheram_ctx_destroy(self._ctx)
             self._ctx = None
+
+
+def pack17(limbs: np.ndarray) -> np.ndarray:
+    """normalised int64 limbs -> the packed host format (17-bit fields, uint32 words)"""
+    a = np.ascontiguousarray(limbs, dtype=np.int64).reshape(-1)
+    out = np.zeros(a.size * 17 // 32, dtype=np.uint32)
+    _check(lib().fheram_pack17(_p(a), a.size, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out
+
+
+def unpack17(packed: np.ndarray, n: int) -> np.ndarray:
+    p = np.ascontiguousarray(packed, dtype=np.uint32).reshape(-1)
+    out = np.zeros(n, dtype=np.int64)
+    _check(lib().fheram_unpack17(p.ctypes.data_as(C.POINTER(C.c_uint32)), n, _p(out)))
+    return out
 
 
 def host_register(a: np.ndarray):
@@ -631,6 +649,15 @@ class Ram:
         P32 = C.POINTER(C.c_int32)
         _check(lib().fheram_ram_read_batch_host_i32(self.h, a.ctypes.data_as(P32), n, keys.h,
                                                     out.reshape(-1).ctypes.data_as(P32)))
+        return out
+
+    def read_batch_host_p17(self, packed: np.ndarray, n: int, keys: EvaluationKeysPrepared, out=None) -> np.ndarray:
+        """addresses in the packed host format (api.pack17), int32 limbs out"""
+        a = np.ascontiguousarray(packed, dtype=np.uint32).reshape(-1)
+        if out is None:
+            out = np.zeros((n, self.params.word_size(), self.params.glwe_len()), dtype=np.int32)
+        _check(lib().fheram_ram_read_batch_host_p17(self.h, a.ctypes.data_as(C.POINTER(C.c_uint32)), n, keys.h,
+                                                    out.reshape(-1).ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
     def read_batch_device(self, addresses: Address, keys: EvaluationKeysPrepared) -> int:

@@ -463,3 +463,40 @@ extern "C" int fheram_decrypt_word(const fheram_params* p, const int64_t* glwe, 
   *value = (i64)std::llround((double)v / std::exp2((double)log_scale));
   return 0;
 }
+
+// ---- packed host format: normalised base-2^17 digits as a little-endian stream of 17-bit two's-complement fields
+// (limb i = bits [17 i, 17 i + 17)); 2.125 bytes per limb against 8 in Poulpy's containers.  n a multiple of 32
+// (every polynomial is), out = n * 17 / 32 words.
+extern "C" int fheram_pack17(const int64_t* limbs, size_t n, uint32_t* out) {
+  if (!limbs || !out || n % 32) { fheram_set_error("fheram_pack17: null argument or n not a multiple of 32"); return FHERAM_ERR_INVALID; }
+  int bad = 0;
+  const size_t groups = n / 32;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for (long long g = 0; g < (long long)groups; g++) {
+    const int64_t* in = limbs + (size_t)g * 32;
+    uint32_t* o = out + (size_t)g * 17;
+    unsigned __int128 acc = 0;
+    int bits = 0, w = 0;
+    for (int k = 0; k < 32; k++) {
+      const int64_t v = in[k];
+      if (v < -65536 || v > 65535) bad = 1;
+      acc |= (unsigned __int128)((uint64_t)v & 0x1ffffu) << bits;
+      bits += 17;
+      while (bits >= 32) { o[w++] = (uint32_t)acc; acc >>= 32; bits -= 32; }
+    }
+  }
+  if (bad) { fheram_set_error("fheram_pack17: limb outside [-2^16, 2^16): only normalised digits can be packed"); return FHERAM_ERR_RANGE; }
+  return 0;
+}
+extern "C" int fheram_unpack17(const uint32_t* packed, size_t n, int64_t* limbs) {
+  if (!packed || !limbs || n % 32) { fheram_set_error("fheram_unpack17: null argument or n not a multiple of 32"); return FHERAM_ERR_INVALID; }
+  for (size_t i = 0; i < n; i++) {
+    const size_t bit = 17 * i, w = bit >> 5;
+    const unsigned sh = (unsigned)(bit & 31);
+    uint64_t two = (uint64_t)packed[w];
+    if (sh > 15) two |= (uint64_t)packed[w + 1] << 32;
+    const uint32_t f = (uint32_t)(two >> sh) & 0x1ffffu;
+    limbs[i] = (int64_t)((int32_t)(f << 15) >> 15);
+  }
+  return 0;
+}

@@ -201,6 +201,7 @@ struct fheram_ctx {
   cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
   // multi-GPU: one context per rank, NCCL communicator over NVLink (fheram_comm_init)
   ncclComm_t comm = nullptr;
+  ncclComm_t comm_prep = nullptr;  // second communicator: all-gather of prepared GGSWs on the upload stream, beside the reads
   int n_ranks = 1, rank = 0;
   double2* d_tw = nullptr;  // tw6 | tw7c | tw8c | tw9 | tw10c
   double2* d_tw16 = nullptr;  // twiddles of the 16-point transform (kernels_ks7.cuh): [16][16] | [128][7]
@@ -374,6 +375,7 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   cudaStreamSynchronize(c->stream);
   wipe_secrets(c);
   cudaStreamSynchronize(c->stream);
+  if (c->comm_prep) { ncclCommDestroy(c->comm_prep); c->comm_prep = nullptr; }
   if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
   c->stage64.release(); c->scratch.release(); c->split_tmp[0].release(); c->split_tmp[1].release();
   for (auto& b : c->opbuf) b.release();
@@ -413,6 +415,8 @@ extern "C" int fheram_comm_init(fheram_ctx* c, int n_ranks, int rank, const uint
   ncclUniqueId u;
   memcpy(&u, id, sizeof(u));
   NC(ncclCommInitRank(&c->comm, n_ranks, u, rank));
+  // collectives of one communicator must not run concurrently: the upload pipeline gets its own
+  NC(ncclCommSplit(c->comm, 0, rank, &c->comm_prep, nullptr));
   c->n_ranks = n_ranks; c->rank = rank;
   return 0;
 }
@@ -420,8 +424,9 @@ extern "C" int fheram_comm_destroy(fheram_ctx* c) {
   if (!c) return 0;
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->comm_prep) NC(ncclCommDestroy(c->comm_prep));
   if (c->comm) NC(ncclCommDestroy(c->comm));
-  c->comm = nullptr; c->n_ranks = 1; c->rank = 0;
+  c->comm = nullptr; c->comm_prep = nullptr; c->n_ranks = 1; c->rank = 0;
   return 0;
 }
 extern "C" int fheram_comm_n_ranks(const fheram_ctx* c) { return c ? c->n_ranks : 0; }
@@ -550,6 +555,19 @@ extern "C" int fheram_host_unregister(void* p) {
 // --------------------------------------------------------------------------------------
 // host <-> device limb conversion
 // --------------------------------------------------------------------------------------
+// packed host format (fheram_pack17): limb i = bits [17 i, 17 i + 17) of a little-endian stream, two's complement
+__global__ void k_unpack17(const uint32_t* __restrict__ in, int* __restrict__ out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const size_t bit = 17 * i, w = bit >> 5;
+    const unsigned sh = (unsigned)(bit & 31);
+    unsigned long long two = in[w];
+    if (sh > 15) two |= (unsigned long long)in[w + 1] << 32;
+    const uint32_t f = (uint32_t)(two >> sh) & 0x1ffffu;
+    out[i] = (int)(f << 15) >> 15;
+  }
+}
 static int upload_i64(fheram_ctx* c, const int64_t* h, size_t n, int* d_out) {
   const size_t chunk = (size_t)64 << 20;  // limbs per staging pass (512 MiB of int64)
   for (size_t off = 0; off < n; off += chunk) {
@@ -766,7 +784,9 @@ static int ext8_mode() {
 // vmp_prepare of n_mat matrices; gal != 1 prepares phi_gal(matrix) (key-switch keys, see k_vmp);
 // order7: frequency order of the 16-point transform (k_prepare7: consumers k_ks7 / k_ext8)
 static int prepare(fheram_ctx* c, const int* raw, long raw_stride, double2* out, long out_stride,
-                   int n_mat, int rows, int cin, int lout, int gal = 1, bool order7 = false) {
+                   int n_mat, int rows, int cin, int lout, int gal = 1, bool order7 = false,
+                   cudaStream_t stream = nullptr) {
+  if (!stream) stream = c->stream;
   PrepArgs a;
   a.raw = raw; a.out = out; a.raw_stride = raw_stride; a.out_stride = out_stride;
   a.rows = rows; a.cin = cin; a.lout = lout; a.tw = c->tw;
@@ -775,10 +795,10 @@ static int prepare(fheram_ctx* c, const int* raw, long raw_stride, double2* out,
     Prep7Args pa;
     pa.p = a; pa.tw16 = c->d_tw16;
     pa.n_polys = n_mat * rows * cin * 2 * lout;
-    k_prepare7<<<(pa.n_polys + 1) / 2, 256, kPrep7Smem, c->stream>>>(pa);
+    k_prepare7<<<(pa.n_polys + 1) / 2, 256, kPrep7Smem, stream>>>(pa);
   } else {
     int grid = n_mat * rows * cin * 2 * lout;
-    k_prepare<<<grid, kThreads, 0, c->stream>>>(a);
+    k_prepare<<<grid, kThreads, 0, stream>>>(a);
   }
   c->launches++;
   CU(cudaGetLastError());
@@ -862,6 +882,11 @@ struct fheram_address {
   int count = 0;
   int* raw = nullptr;        // [count][n_ggsw] raw GGSW, int32
   double2* prep = nullptr;   // [count][n_ggsw] prepared GGSW
+  // split layout of the sharded host pipeline (prep1 != nullptr): prep = [count][coord_len[0]] prepared GGSWs of the
+  // first coordinate (every rank needs them for its local stage: all-gathered), prep1 = [own reads][coord_len[1]] of
+  // the second coordinate, which only the finishing rank needs (address `prep1_first` of the set is its entry 0)
+  double2* prep1 = nullptr;
+  int prep1_first = 0;
   // CoordinatePrepared::prepare_inv of every digit (src/ram.rs:260-271,278-289): a cache of the address handle,
   // built by read_prepare_write (off the critical path of the write that follows) or lazily by write
   mutable int* inv_raw = nullptr;    // [n_ggsw] GGSW(X^+digit)
@@ -1200,8 +1225,8 @@ extern "C" int fheram_ram_destroy(fheram_ram* r) {
   if (r->wpin) { cudaStreamSynchronize(r->c->stream); cudaFreeHost(r->wpin); cudaEventDestroy(r->wcopied); }
   r->bufA.release(); r->bufB.release(); r->partial.release(); r->result.release(); r->wbuf.release(); r->wstage.release(); r->all.release(); r->xchg.release(); r->part_all.release();
   for (auto& s : r->pipe.sets) {
-    cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
-    s.a.raw = nullptr; s.a.prep = nullptr;
+    cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep); cudaFree(s.a.prep1);
+    s.a.raw = nullptr; s.a.prep = nullptr; s.a.prep1 = nullptr;
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.freed) cudaEventDestroy(s.freed);
   }
@@ -1549,8 +1574,9 @@ static int ram_local_stage(fheram_ram* r, const fheram_address* addr, int first_
   TRY(r->partial.ensure(sizeof(int) * (size_t)B * ws * L));
   int* A = (int*)r->bufA.p;
   int* Bb = (int*)r->bufB.p;
-  const double2* mats = addr->prep + (size_t)first_addr * d.n_ggsw * c->ggsw_prep_len();
-  const long mat_stride = (long)d.n_ggsw * c->ggsw_prep_len();
+  // matrices of the first coordinate of address first_addr, and the distance to the next address
+  const long mat_stride = (long)(addr->prep1 ? d.coord_len[0] : d.n_ggsw) * c->ggsw_prep_len();
+  const double2* mats = addr->prep + (size_t)first_addr * mat_stride;
   const int lg_total = ilog2(d.n_glwe);          // two-sided levels of the full tree
   const int one_sided = d.log_n - lg_total;      // levels with a single non-empty child
   if (d.n_coord == 1) {
@@ -1626,8 +1652,10 @@ static int ram_finish_stage(fheram_ram* r, const int* gathered, int n_total, int
     packed = gathered + (size_t)first * ws * L;
   }
   const int c1 = first_coord_ggsw(d, 1);
-  const double2* mats = addr->prep + ((size_t)(first_addr + first) * d.n_ggsw + c1) * c->ggsw_prep_len();
-  const long mat_stride = (long)d.n_ggsw * c->ggsw_prep_len();
+  const long mat_stride = (long)(addr->prep1 ? d.coord_len[1] : d.n_ggsw) * c->ggsw_prep_len();
+  const double2* mats = addr->prep1
+      ? addr->prep1 + (size_t)(first_addr + first - addr->prep1_first) * mat_stride
+      : addr->prep + ((size_t)(first_addr + first) * d.n_ggsw + c1) * c->ggsw_prep_len();
   if (store_tree) {
     TRY(run_ext_chain(c, groups, packed, nullptr, 0, r->tree, mats, d.coord_len[1], ws, mat_stride));
     CU(cudaMemcpyAsync(res, r->tree, sizeof(int) * (size_t)groups * L, cudaMemcpyDeviceToDevice, c->stream));  // src/ram.rs:535
@@ -1753,7 +1781,8 @@ extern "C" int fheram_ram_read(fheram_ram* r, const fheram_address* addr, const 
 // GGSWs are all-gathered over NVLink (NCCL, in place), every rank rotates + packs its own polynomials for all
 // n_ranks * nb reads of the chunk, the packed partials are exchanged with one all-to-all, and each rank finishes its
 // own nb reads (top log2 n_ranks packer levels, second coordinate, trace).
-static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_bytes, int n, const fheram_keys* k,
+// in_fmt: 8 (int64 limbs), 4 (int32 limbs) or 17 (packed 17-bit fields, fheram_pack17)
+static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_fmt, int n, const fheram_keys* k,
                                 void* out_host, int out_bytes) {
   if (!r || !ggsw_host || !k || !out_host || n < 1) return fail(FHERAM_ERR_INVALID, "bad argument");
   if (k->c != r->c) return fail(FHERAM_ERR_INVALID, "handles belong to different contexts");
@@ -1768,7 +1797,7 @@ static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_byt
   const int ws = c->params.word_size;
   const long L = c->ct_stride();
   const size_t per_addr = (size_t)d.n_ggsw * c->ggsw_raw_len();                   // limbs per address
-  const size_t prep_addr = (size_t)d.n_ggsw * c->ggsw_prep_len() * sizeof(double2); // prepared bytes per address
+  const size_t glen = (size_t)c->ggsw_prep_len();                                   // double2 per prepared GGSW
   int chunk = batch_chunk(r);   // reads per rank and chunk: the local stage handles G * chunk reads of 1 / G of the RAM
   if (chunk > n) chunk = n;
   // staging buffers, events and the copy stream are created once per RAM handle and reused
@@ -1788,12 +1817,14 @@ static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_byt
   if (!hp.down_stream) CU(cudaStreamCreateWithFlags(&hp.down_stream, cudaStreamNonBlocking));
   if (hp.cap < chunk) {
     for (auto& s : hp.sets) {
-      cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep);
-      s.stage = nullptr; s.a.raw = nullptr; s.a.prep = nullptr;
+      cudaFree(s.stage); cudaFree(s.a.raw); cudaFree(s.a.prep); cudaFree(s.a.prep1);
+      s.stage = nullptr; s.a.raw = nullptr; s.a.prep = nullptr; s.a.prep1 = nullptr;
       s.a.c = c;
       CU(cudaMalloc(&s.stage, sizeof(long long) * chunk * per_addr));       // int64 staging of the own slice
       CU(cudaMalloc(&s.a.raw, sizeof(int) * chunk * per_addr));             // raw limbs of the own slice
-      CU(cudaMalloc(&s.a.prep, (size_t)G * chunk * prep_addr));             // prepared GGSWs of every rank's slice
+      // prepared GGSWs: first coordinate of every rank's slice (all-gathered), second coordinate of the own slice
+      CU(cudaMalloc(&s.a.prep, (size_t)G * chunk * d.coord_len[0] * glen * sizeof(double2)));
+      if (d.n_coord > 1) CU(cudaMalloc(&s.a.prep1, (size_t)chunk * d.coord_len[1] * glen * sizeof(double2)));
       if (!s.copied) CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
       if (!s.freed) CU(cudaEventCreateWithFlags(&s.freed, cudaEventDisableTiming));
     }
@@ -1816,13 +1847,32 @@ static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_byt
   const int n_chunks = (int)start.size() - 1;
   const char* in = (const char*)ggsw_host;
   char* out = (char*)out_host;
+  // upload side of chunk ci, all on the copy stream: host -> device, limb conversion, CoordinatePrepared::prepare of
+  // the OWN addresses, all-gather of the first-coordinate matrices (NVLink, own communicator); it runs beside the reads
+  // of chunk ci - 1 on the compute stream
   auto issue_copy = [&](int ci) -> int {
     Set& s = sets[ci & 1];
     const int b0 = start[ci], nb = start[ci + 1] - b0;
     if (ci >= 2) CU(cudaStreamWaitEvent(copy_stream, s.freed, 0));
-    void* dst = in_bytes == 8 ? (void*)s.stage : (void*)s.a.raw;  // int32 limbs land where the prepare kernel reads them
-    CU(cudaMemcpyAsync(dst, in + (size_t)b0 * per_addr * in_bytes, (size_t)nb * per_addr * in_bytes,
-                       cudaMemcpyHostToDevice, copy_stream));
+    void* dst = in_fmt == 4 ? (void*)s.a.raw : (void*)s.stage;  // int32 limbs land where the prepare kernel reads them
+    const size_t addr_bytes = in_fmt == 17 ? per_addr * 17 / 8 : per_addr * in_fmt;  // per_addr is a multiple of 4096
+    CU(cudaMemcpyAsync(dst, in + (size_t)b0 * addr_bytes, (size_t)nb * addr_bytes, cudaMemcpyHostToDevice, copy_stream));
+    if (in_fmt == 8) {
+      k_i64_to_i32<<<c->sm_count * 8, 256, 0, copy_stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
+      c->launches++;
+    } else if (in_fmt == 17) {
+      k_unpack17<<<c->sm_count * 8, 256, 0, copy_stream>>>((const uint32_t*)s.stage, s.a.raw, (size_t)nb * per_addr);
+      c->launches++;
+    }
+    // one "matrix" of the prepare kernel = the coord_len[.] consecutive GGSWs of one coordinate of one address
+    const int n0 = d.coord_len[0], n1 = d.n_coord > 1 ? d.coord_len[1] : 0;
+    double2* own = s.a.prep + (size_t)r->shard * nb * n0 * glen;
+    TRY(prepare(c, s.a.raw, (long)per_addr, own, (long)(n0 * glen), nb, n0 * d.dnum_ct, 2, d.size_addr, 1,
+                ext8_mode() != 0, copy_stream));
+    if (n1)
+      TRY(prepare(c, s.a.raw + (size_t)n0 * c->ggsw_raw_len(), (long)per_addr, s.a.prep1, (long)(n1 * glen), nb,
+                  n1 * d.dnum_ct, 2, d.size_addr, 1, ext8_mode() != 0, copy_stream));
+    if (G > 1) NC(ncclAllGather(own, s.a.prep, (size_t)nb * n0 * glen * sizeof(double2), ncclChar, c->comm_prep, copy_stream));
     CU(cudaEventRecord(s.copied, copy_stream));
     return 0;
   };
@@ -1832,15 +1882,8 @@ static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_byt
     Set& s = sets[ci & 1];
     const int b0 = start[ci], nb = start[ci + 1] - b0;
     s.a.count = G * nb;
+    s.a.prep1_first = r->shard * nb;
     CUC(cudaStreamWaitEvent(c->stream, s.copied, 0));
-    if (in_bytes == 8) {
-      k_i64_to_i32<<<c->sm_count * 8, 256, 0, c->stream>>>(s.stage, s.a.raw, (size_t)nb * per_addr, c->d_err);
-      c->launches++;
-    }
-    // prepare the own nb addresses into block `shard` of the chunk's prepared set, then gather the other blocks
-    double2* own = s.a.prep + (size_t)r->shard * nb * d.n_ggsw * c->ggsw_prep_len();
-    TRYC(prepare_ggsw(c, s.a.raw, own, nb * d.n_ggsw));
-    if (G > 1) NCC(ncclAllGather(own, s.a.prep, (size_t)nb * prep_addr, ncclChar, c->comm, c->stream));
     TRYC(ram_local_stage(r, &s.a, 0, G * nb, k, false));
     const int* gathered = (const int*)r->partial.p;
     if (G > 1) {
@@ -1882,6 +1925,11 @@ static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_byt
 extern "C" int fheram_ram_read_batch_host(fheram_ram* r, const int64_t* ggsw_host, int n, const fheram_keys* k,
                                           int64_t* out_host) {
   return read_batch_host_impl(r, ggsw_host, 8, n, k, out_host, 8);
+}
+// packed host format: addresses as 17-bit fields (fheram_pack17: 2.125 bytes per limb), results as int32 limbs
+extern "C" int fheram_ram_read_batch_host_p17(fheram_ram* r, const uint32_t* ggsw_packed, int n, const fheram_keys* k,
+                                              int32_t* out_host) {
+  return read_batch_host_impl(r, ggsw_packed, 17, n, k, out_host, 4);
 }
 // compact host format: the same limbs as int32 (normalised digits fit 17 bits), addresses and results
 extern "C" int fheram_ram_read_batch_host_i32(fheram_ram* r, const int32_t* ggsw_host, int n, const fheram_keys* k,

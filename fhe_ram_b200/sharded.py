@@ -185,9 +185,10 @@ class ShardedRamLib:
     def read_batch_device(self, addrs, keys) -> int:
         return self.ram.read_batch_device(addrs, keys)
 
-    def read_batch_host(self, my_addr_limbs, n, keys, out=None, i32=False):
-        """my_addr_limbs = THIS rank's n addresses (host limbs); returns this rank's n results"""
-        fn = self.ram.read_batch_host_i32 if i32 else self.ram.read_batch_host
+    def read_batch_host(self, my_addr_limbs, n, keys, out=None, fmt="i64"):
+        """my_addr_limbs = THIS rank's n addresses in host format `fmt` (i64 / i32 limbs, p17 packed); returns this
+        rank's n results"""
+        fn = {"i64": self.ram.read_batch_host, "i32": self.ram.read_batch_host_i32, "p17": self.ram.read_batch_host_p17}[fmt]
         return fn(my_addr_limbs, n, keys, out)
 
     def read_prepare_write(self, addr, keys) -> np.ndarray:

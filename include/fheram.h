@@ -169,6 +169,15 @@ int fheram_ram_read_batch_host(fheram_ram *r, const int64_t *ggsw, int n, const 
  * them as int64): half the bytes over PCIe in both directions and no conversion pass.  Not range checked. */
 int fheram_ram_read_batch_host_i32(fheram_ram *r, const int32_t *ggsw, int n, const fheram_keys *k,
                                    int32_t *out);
+/* packed host format: addresses as a little-endian stream of 17-bit two's-complement fields (limb i = bits
+ * [17 i, 17 i + 17); fheram_pack17 below), 2.125 bytes per limb: what keeps 8 GPUs fed over one host's PCIe;
+ * results as int32 limbs */
+int fheram_ram_read_batch_host_p17(fheram_ram *r, const uint32_t *ggsw_packed, int n, const fheram_keys *k,
+                                   int32_t *out);
+/* host-side packing / unpacking of normalised limbs (n a multiple of 32, packed = n * 17 / 32 words);
+ * fheram_pack17 fails with FHERAM_ERR_RANGE on a limb outside [-2^16, 2^16) */
+int fheram_pack17(const int64_t *limbs, size_t n, uint32_t *packed);
+int fheram_unpack17(const uint32_t *packed, size_t n, int64_t *limbs);
 /* device-resident variant: result left in the RAM's result arena (int32 device limbs,
  * [n][word_size][limb][col][N]); returns the device pointer.  No host copies. */
 int fheram_ram_read_batch_device(fheram_ram *r, const fheram_address *addr, const fheram_keys *k,

@@ -162,3 +162,27 @@ def test_unsupported_parameters_rejected_before_device(built):
         with pytest.raises(fr.FheRamError) as e:
             fr.Parameters.new(**over).module()
         assert e.value.code in (-1, -5)
+
+
+def test_pack17_roundtrip_and_range(built):
+    """packed host format: 17-bit two's-complement fields, limb i at bits [17 i, 17 i + 17)"""
+    import ctypes as C
+    from fhe_ram_b200 import api
+    rng = np.random.default_rng(17)
+    a = rng.integers(-(1 << 16), 1 << 16, size=64 * 4096, dtype=np.int64)
+    a[:4] = [-(1 << 16), (1 << 16) - 1, 0, -1]
+    p = api.pack17(a)
+    assert p.dtype == np.uint32 and p.size == a.size * 17 // 32
+    assert np.array_equal(api.unpack17(p, a.size), a)
+    # bit layout pinned independently of the C code
+    bits = np.zeros(a[:64].size * 17, dtype=np.uint8)
+    for i, v in enumerate(a[:64]):
+        for b in range(17):
+            bits[17 * i + b] = (int(v) >> b) & 1
+    words = np.packbits(bits.reshape(-1, 32)[:, ::-1], axis=1).view(">u4").reshape(-1)
+    assert np.array_equal(words.astype(np.uint32), p[:words.size])
+    bad = a.copy()
+    bad[5] = 1 << 16
+    with pytest.raises(api.FheRamError) as e:
+        api.pack17(bad)
+    assert e.value.code == -6

@@ -231,6 +231,10 @@ def test_host_buffer_batch_pipeline(scenario, gpu_keys):
     # compact host format (int32 limbs in and out): the same limbs
     got32 = ram.read_batch_host_i32(limbs.astype(np.int32), len(idxs), keys)
     assert got32.dtype == np.int32 and np.array_equal(got32.astype(np.int64), got)
+    # packed host format (17-bit fields)
+    from fhe_ram_b200 import api
+    got17 = ram.read_batch_host_p17(api.pack17(limbs), len(idxs), keys)
+    assert np.array_equal(got17, got32)
     bad = limbs.copy()
     bad[3, 5] = 1 << 40
     with pytest.raises(fr.FheRamError) as e:

@@ -49,9 +49,13 @@ def _worker(rank, world, port, out_dir):
     got = lib.read_batch_host(limbs, hi - lo, keys)
     if not np.array_equal(got, want[lo:hi]):
         fails.append("lib read_batch_host (int64)")
-    got = lib.read_batch_host(limbs.astype(np.int32), hi - lo, keys, i32=True)
+    got = lib.read_batch_host(limbs.astype(np.int32), hi - lo, keys, fmt="i32")
     if not np.array_equal(got.astype(np.int64), want[lo:hi]):
         fails.append("lib read_batch_host (int32)")
+    from fhe_ram_b200 import api
+    got = lib.read_batch_host(api.pack17(limbs), hi - lo, keys, fmt="p17")
+    if not np.array_equal(got.astype(np.int64), want[lo:hi]):
+        fails.append("lib read_batch_host (packed 17-bit)")
     a_w = addrs[2 % B]
     rpw = lib.read_prepare_write(a_w, keys)
     want_rpw = ref.read_prepare_write(a_w, keys)
