@@ -255,11 +255,7 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(K_EXT_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 2, false)));
   CU(cudaFuncSetAttribute(K_TRACE_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
   CU(cudaFuncSetAttribute(K_COMBINE2_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(3, 1, true)));
-  CU(cudaFuncSetAttribute(k_ext2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt2Smem));
   CU(cudaFuncSetAttribute(k_ext3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt3Smem));
-  CU(cudaFuncSetAttribute(k_ks2<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
-  CU(cudaFuncSetAttribute(k_ks3<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
-  CU(cudaFuncSetAttribute(k_ks3<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs3Smem));
   CU(cudaFuncSetAttribute(k_ks7<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_ks7<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
@@ -270,7 +266,6 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks5<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks4<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
   CU(cudaFuncSetAttribute(k_ks4<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs4Smem));
-  CU(cudaFuncSetAttribute(k_ks2<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs2Smem));
   return 0;
 }
 
@@ -336,7 +331,6 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
     q[b - 512] = make_double2(dx * r, sx * r);
   }
   CU(cudaMemcpyToSymbol(c_tw_lo, lo.data(), sizeof(double2) * 64));
-  CU(cudaMemcpyToSymbol(c_tw3, hi.data(), sizeof(double2) * 256));  // tw6 | tw7c | tw8c
   CU(cudaMalloc(&c->d_tw, sizeof(double2) * hi.size()));
   CU(cudaMemcpy(c->d_tw, hi.data(), sizeof(double2) * hi.size(), cudaMemcpyHostToDevice));
   c->tw.tw6 = c->d_tw;
@@ -670,14 +664,8 @@ static int launch_split(fheram_ctx* c, K kernel, const VmpArgs& a, size_t smem, 
   CU(cudaGetLastError());
   return 0;
 }
-// key-switch kernels built for two CTAs per SM (kernels_ks2.cuh); FHERAM_KS2=0 selects k_vmp
-static bool use_ks2() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FHERAM_KS2"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-// word-domain key-switch kernels (kernels_ks3.cuh); FHERAM_KS3=0 falls back to k_ks2 / k_vmp,
-// FHERAM_KS3=2 uses them for narrow launches as well
+// word-domain key-switch kernels with two CTAs per SM (k_ks4; k_ext3 when FHERAM_EXT8=0): FHERAM_KS3=0 falls back to
+// k_vmp, FHERAM_KS3=2 uses them for narrow launches as well
 static int ks3_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FHERAM_KS3"); v = e ? atoi(e) : 1; }
@@ -746,14 +734,8 @@ static int launch_ks7(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   CU(cudaGetLastError());
   return 0;
 }
-// FHERAM_KSGEN=3 selects k_ks3 instead of the pipelined k_ks4 (kernels_ks4.cuh) where ks3_mode() applies
-static bool use_ks4() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FHERAM_KSGEN"); v = (e && atoi(e) == 3) ? 0 : 1; }
-  return v == 1;
-}
 template <typename K>
-static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls, size_t smem = kKs2Smem) {
+static int launch_ks2(fheram_ctx* c, K kernel, const VmpArgs& a, int cls, size_t smem) {
   if (a.n_items <= 0) return 0;
   int grid = a.n_items < 2 * c->sm_count ? a.n_items : 2 * c->sm_count;
   size_t e0 = 0;
@@ -1045,7 +1027,6 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
     return 0;
   }
   if (ks3_mode() >= 1 && n_items > c->sm_count) return launch_ks2(c, k_ext3, a, KC_EXT, kExt3Smem);
-  if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ext2, a, KC_EXT, kExt2Smem);
   return launch(c, K_EXT, a, smem_bytes(3, 2, false), KC_EXT);
 }
 // chain of { glwe_rsh(1); automorphism_add with trace key i } for i in [g0, g1)
@@ -1081,8 +1062,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   }
   if (ks5_mode() >= 1 && use_ks6(c, n_items)) return launch_ks6(c, k_ks6<MODE_TRACE>, a, KC_TRACE);
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count)) return launch_ks5(c, k_ks5<MODE_TRACE>, a, KC_TRACE);
-  if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
-  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
   if (use_split(c, n_items)) {
     const size_t bytes = sizeof(int) * (size_t)n_items * c->ct_stride();
     TRY(c->split_tmp[0].ensure(bytes));
@@ -1103,9 +1083,7 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
   }
   // wide launches: two lean CTAs per SM overlap each other's phases; narrow ones (at most one
   // item per SM) finish sooner with the single-CTA kernel
-  if (ks3_mode() == 1 && n_items > c->sm_count && use_ks4()) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
-  if (ks3_mode() == 1 && n_items > c->sm_count) return launch_ks2(c, k_ks3<MODE_TRACE>, a, KC_TRACE, kKs3Smem);
-  if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_TRACE>, a, KC_TRACE);
+  if (ks3_mode() == 1 && n_items > c->sm_count) return launch_ks2(c, k_ks4<MODE_TRACE>, a, KC_TRACE, kKs4Smem);
   return launch(c, K_TRACE, a, smem_bytes(3, 1, true), KC_TRACE);
 }
 // GLWEPacker::combine, both operands present, at tree level `level` (0-based absolute):
@@ -1130,12 +1108,9 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   // one item per SM where two CTAs per item no longer fit (75 .. sm_count items): 37-39 us against 45 us of k_vmp
   if (ks5_mode() == 2 || (ks5_mode() == 1 && n_items <= c->sm_count && 2 * n_items > c->sm_count))
     return launch_ks5(c, k_ks5<MODE_COMBINE2>, a, KC_COMBINE2);
-  if (ks3_mode() >= 2 && use_ks4()) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
-  if (ks3_mode() >= 2) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
+  if (ks3_mode() >= 2) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
   if (use_split(c, n_items)) return launch_split(c, K_COMBINE2_S, a, smem_bytes(3, 1, true), KC_COMBINE2);
-  if (ks3_mode() == 1 && n_items > c->sm_count && use_ks4()) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
-  if (ks3_mode() == 1 && n_items > c->sm_count) return launch_ks2(c, k_ks3<MODE_COMBINE2>, a, KC_COMBINE2, kKs3Smem);
-  if (use_ks2() && n_items > c->sm_count) return launch_ks2(c, k_ks2<MODE_COMBINE2>, a, KC_COMBINE2);
+  if (ks3_mode() == 1 && n_items > c->sm_count) return launch_ks2(c, k_ks4<MODE_COMBINE2>, a, KC_COMBINE2, kKs4Smem);
   return launch(c, K_COMBINE2, a, smem_bytes(3, 1, true), KC_COMBINE2);
 }
 
@@ -1840,9 +1815,22 @@ static int read_batch_host_impl(fheram_ram* r, const void* ggsw_host, int in_fmt
   if (G > 1) TRYC(r->xchg.ensure(sizeof(int) * (size_t)G * chunk * ws * L));
   Set* sets = hp.sets;
   cudaStream_t copy_stream = hp.copy_stream;
-  // chunk boundaries: the first chunks are small (their upload is not overlapped with anything), then full size
+  // chunk boundaries: the first chunk is small (its upload overlaps nothing), the sizes then double up to the full
+  // chunk, and the schedule is laid out from the END so that no tiny chunk (narrow launches) trails a batch that is
+  // not a multiple of the chunk: n = 128 -> 8, 8, 16, 32, 64;  n = 1024 -> 8, 8, 16, 32, 64, 64, ...
   std::vector<int> start;
-  for (int b = 0, sz = chunk >= 64 ? 16 : (chunk >= 8 ? chunk / 4 : chunk); b < n; b += sz, sz = sz * 2 < chunk ? sz * 2 : chunk) start.push_back(b);
+  {
+    std::vector<int> sizes;
+    int left = n, sz = chunk;
+    while (left > 0) {
+      const int take = left < sz ? left : sz;
+      sizes.push_back(take);
+      left -= take;
+      if (left < 2 * sz && sz > 8) sz = sz / 2 > 8 ? sz / 2 : 8;  // ramp down towards the front of the batch
+    }
+    int b = 0;
+    for (size_t i = sizes.size(); i-- > 0;) { start.push_back(b); b += sizes[i]; }
+  }
   start.push_back(n);
   const int n_chunks = (int)start.size() - 1;
   const char* in = (const char*)ggsw_host;

@@ -1,7 +1,9 @@
 """Every kernel generation behind the same C ABI must give the same limbs as the oracle.
 
-The library picks a kernel per launch from the launch width (narrow: column-split k_vmp / k_ks6 / k_ks5,
-wide: k_ext3 / k_ks4; the default selection is what test_gpu_parity.py itself runs).  The small parity cases of test_gpu_parity.py only produce narrow launches, so
+The library picks a kernel per launch from the launch width (external products: k_ext8 always; key switches: narrow
+k_ks6 / k_ks5, wide k_ks7 / k_ks4; the default selection is what test_gpu_parity.py itself runs, and the wide kernels
+are checked at BASELINE sizes in test_gpu_baseline_sizes.py).  The small parity cases of test_gpu_parity.py only
+produce narrow launches, so
 each variant is forced through the whole limb-level parity set (external product, chains, trace,
 packer, read / read_prepare_write / write at four parameter sets, batched, sharded) in a
 subprocess: the selection knobs are read once per process.
@@ -22,20 +24,20 @@ SELECT = ("test_external_product_matches_oracle or test_external_product_adversa
           "test_sharded_stages_on_one_gpu")
 
 VARIANTS = {
-    # word-domain key switch, in-place accumulation + double-buffered tiles (k_ks4) and padded k_ext3
-    "ks4_ext3": {"FHERAM_KS3": "2", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
+    # word-domain key switch with in-place accumulation and two tiles in flight (k_ks4) for every key-switch launch
+    "ks4": {"FHERAM_KS3": "2", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
     # 16-point-per-thread transform with two exchanges, two polynomials per CTA (k_ks7) for every trace chain
     "ks7": {"FHERAM_KS7": "2"},
     # the same kernel for the packer's two-sided combine as well (k_ks7<MODE_COMBINE2>)
     "ks7c": {"FHERAM_KS7": "2", "FHERAM_KS7C": "2"},
-    # word-domain key switch with register accumulators (k_ks3)
-    "ks3": {"FHERAM_KS3": "2", "FHERAM_KSGEN": "3", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
     # one operation per SM, 512 threads, tiles parked in tensor memory (k_ks5), trace and combine
     "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0", "FHERAM_KS7": "0"},
-    # digit-domain two-CTA kernels (k_ks2 / k_ext2) and the single-CTA k_vmp without column split
-    "ks2_vmp": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_SPLIT": "0", "FHERAM_KS7": "0"},
-    # column-split k_vmp for every narrow operation (two CTAs per operation, one launch per chain step)
+    # column-split k_vmp for every narrow key switch (two CTAs per operation, one launch per chain step)
     "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
+    # round-1 external-product kernels (k_ext3 forced for every launch, GGSWs prepared in its frequency order)
+    "ext3": {"FHERAM_EXT8": "0", "FHERAM_KS3": "2"},
+    # round-1 narrow external product (column-split k_vmp<EXT>) and the single-CTA k_vmp without column split
+    "ext_vmp": {"FHERAM_EXT8": "0", "FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_SPLIT": "0"},
 }
 
 
