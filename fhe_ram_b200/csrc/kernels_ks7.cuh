@@ -89,8 +89,13 @@ __device__ __forceinline__ void forward16(double2 (&x)[16], const T16& c, T3&& t
   gsync128(c.g);
 #pragma unroll
   for (int m = 0; m < 16; m++) x[m] = c.buf[136 * a + 8 * m + cc + (m >> 1)];
+  // pass-2 twiddles of block a: zeta(s, 2 j + 1) = i zeta(s, 2 j), so only the even entries are loaded (8 instead of 15
+  // LDS.128 per transform: the table reads were a fifth of the shared-memory wavefronts of a key switch)
   const double2* ta = c.tw2 + 16 * a;
-  fwd16<0>(x, [&](int sl, int bl) { return ta[(1 << sl) + bl]; });
+  fwd16<0>(x, [&](int sl, int bl) {
+    const double2 w = ta[(1 << sl) + (bl & ~1)];
+    return (sl > 0 && (bl & 1)) ? mul_i(w) : w;
+  });
 #pragma unroll
   for (int m = 0; m < 16; m++) c.buf[136 * a + 8 * m + cc + (m >> 1)] = x[m];
   __syncwarp();
@@ -115,7 +120,10 @@ __device__ __forceinline__ void inverse16(double2 (&x)[16], const T16& c, T3&& t
 #pragma unroll
   for (int m = 0; m < 16; m++) x[m] = c.buf[136 * a + 8 * m + cc + (m >> 1)];
   const double2* ta = c.tw2 + 16 * a;
-  inv16<0>(x, [&](int sl, int bl) { return ta[(1 << sl) + bl]; });
+  inv16<0>(x, [&](int sl, int bl) {
+    const double2 w = ta[(1 << sl) + (bl & ~1)];
+    return (sl > 0 && (bl & 1)) ? mul_i(w) : w;
+  });
 #pragma unroll
   for (int m = 0; m < 16; m++) c.buf[136 * a + 8 * m + cc + (m >> 1)] = x[m];
   gsync128(c.g);

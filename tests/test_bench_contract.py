@@ -26,7 +26,7 @@ def test_reference_arm_line(built):
 
 def test_committed_b200_line_has_the_contract_keys():
     """the last GPU-arm line committed under profiles/ (written by bench.py on the B200 box)"""
-    files = sorted((ROOT / "profiles").glob("r1*_bench_b1024.json"))
+    files = sorted((ROOT / "profiles").glob("r2*_bench1.json"))
     assert files, "no committed bench line"
     line = json.loads(files[-1].read_text().strip().splitlines()[-1])
     assert COMMON | {"roofline", "clocks"} <= set(line)
@@ -34,6 +34,8 @@ def test_committed_b200_line_has_the_contract_keys():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf)
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["scaling"] == "strong" and line["e2e"]["value"] != line["value"]
+    assert {"value", "cores", "kind", "sample", "one_thread_read_s"} <= set(line["cpu_baseline"]) if line["cpu_baseline"] else True
     assert line["gpu_launches"] > 0 and not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
