@@ -80,6 +80,8 @@ SIGNATURES = {
     "fheram_host_unregister": (C.c_int, [_V]),
     "fheram_keys_prepare": (C.c_int, [_V, _P64, _P64, _P64, _PV]),
     "fheram_keys_destroy": (C.c_int, [_V]),
+    "fheram_keys_encrypt_sk": (C.c_int, [_V, _P64, _V, _V, _PV]),
+    "fheram_keys_download_raw": (C.c_int, [_V, _P64, _P64, _P64]),
     "fheram_address_load": (C.c_int, [_V, _P64, _PV]),
     "fheram_address_load_batch": (C.c_int, [_V, _P64, C.c_int, _PV]),
     "fheram_address_alloc": (C.c_int, [_V, C.c_int, _PV]),
@@ -409,6 +411,25 @@ class EvaluationKeysPrepared:
                                          _p(keys.gglwe_to_ggsw_key), _p(keys.atk_ggsw_inv), C.byref(h)))
         self.h = h
         return self
+
+    @classmethod
+    def encrypt_sk_gpu(cls, params: Parameters, sk: "GLWESecret", source_xa: "Source", source_xe: "Source") -> "EvaluationKeysPrepared":
+        """EvaluationKeys::encrypt_sk (src/keys.rs:135-180) + prepare on the device: the limbs of
+        `EvaluationKeys.encrypt_sk` from the same Sources, resident and prepared"""
+        k = cls(params)
+        h = C.c_void_p()
+        _check(lib().fheram_keys_encrypt_sk(params.module(), _p(sk.data), source_xa.h, source_xe.h, C.byref(h)))
+        k.h = h
+        return k
+
+    def download_raw(self) -> "EvaluationKeys":
+        """raw limbs of keys made by encrypt_sk_gpu (fheram_keygen's layout)"""
+        p = self.params
+        atk = np.zeros(p.n_trace_keys() * p.atk_len(), dtype=np.int64)
+        tsk = np.zeros(p.evk_inv_len(), dtype=np.int64)
+        inv = np.zeros(p.evk_inv_len(), dtype=np.int64)
+        _check(lib().fheram_keys_download_raw(self.h, _p(atk), _p(tsk), _p(inv)))
+        return EvaluationKeys(p, atk, tsk, inv)
 
     def close(self):
         if self.h is not None:

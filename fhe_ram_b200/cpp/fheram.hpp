@@ -97,6 +97,12 @@ struct EvaluationKeys {  // src/keys.rs:21-25
 class EvaluationKeysPrepared {  // src/keys.rs:27-71
  public:
   static EvaluationKeysPrepared alloc(Parameters& p) { return EvaluationKeysPrepared(p); }
+  // EvaluationKeys::encrypt_sk (:135-180) + prepare on the device: same limbs, keys never leave the GPU
+  static EvaluationKeysPrepared encrypt_sk_device(Parameters& p, const GLWESecret& sk, Source& xa, Source& xe) {
+    EvaluationKeysPrepared k(p);
+    check(fheram_keys_encrypt_sk(p.module(), sk.data.data(), xa.raw(), xe.raw(), &k.h_));
+    return k;
+  }
   void prepare(const EvaluationKeys& k) {
     check(fheram_keys_prepare(p_.module(), k.atk_glwe.data(), k.gglwe_to_ggsw_key.data(), k.atk_ggsw_inv.data(), &h_));
   }

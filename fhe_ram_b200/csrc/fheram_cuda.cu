@@ -210,7 +210,7 @@ struct fheram_ctx {
   uint64_t launches = 0;
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
-  DevBuf enc_buf[12];  // operands of the encryption kernels, kept between calls (cudaFree synchronizes the device)
+  DevBuf enc_buf[15];  // operands of the encryption kernels, kept between calls (cudaFree synchronizes the device)
   uint64_t enc_stats[3] = {0, 0, 0};  // noise draws sampled on the device / patched by the host / streams resampled on the host
   DevBuf opbuf[3];  // op-level entry points
   DevBuf split_tmp[2];  // ping-pong ciphertexts of the column-split (latency) schedules
@@ -801,7 +801,33 @@ struct fheram_keys {
   double2* atk7 = nullptr;     // trace keys prepared in the frequency order of k_ks7
   double2* atk_inv = nullptr;  // prepared atk_ggsw_inv
   double2* tsk = nullptr;      // prepared tsk_ggsw_inv
+  int* raw = nullptr;          // fheram_keys_encrypt_sk: the raw keys [atk x log_n | tsk | atk_inv] (fheram_keys_download_raw)
 };
+
+// EvaluationKeysPrepared::prepare (src/keys.rs:57-71) from raw int32 keys already on the device:
+// d_atk = [log_n] trace keys, d_tsk, d_inv (layouts of include/fheram.h)
+static int keys_prepare_device(fheram_ctx* c, const int* d_atk, const int* d_tsk, const int* d_inv, fheram_keys* k) {
+  const Derived& d = c->d;
+  const size_t atk_raw = (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n;
+  const size_t inv_raw = (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n;
+  CU(cudaMalloc(&k->atk, sizeof(double2) * c->atk_prep_len() * d.log_n));
+  CU(cudaMalloc(&k->atk7, sizeof(double2) * c->atk_prep_len() * d.log_n));
+  CU(cudaMalloc(&k->atk_inv, sizeof(double2) * c->evk_inv_prep_len()));
+  CU(cudaMalloc(&k->tsk, sizeof(double2) * c->evk_inv_prep_len()));
+  // trace key i is stored as phi_{g_i}(key): the kernels transform phi_g(x) and get phi_g(KS(x)); once per
+  // transform family (frequency orders of k_prepare and k_prepare7)
+  for (int i = 0; i < d.log_n; i++) {
+    const int gal = (int)((galois(d.log_n, i) + 2 * kN) % (2 * kN));
+    TRY(prepare(c, d_atk + (size_t)i * atk_raw, (long)atk_raw, k->atk + (size_t)i * c->atk_prep_len(),
+                c->atk_prep_len(), 1, d.dnum_ct, 1, d.size_evk_trace, gal));
+    TRY(prepare(c, d_atk + (size_t)i * atk_raw, (long)atk_raw, k->atk7 + (size_t)i * c->atk_prep_len(),
+                c->atk_prep_len(), 1, d.dnum_ct, 1, d.size_evk_trace, gal, true));
+  }
+  TRY(prepare(c, d_inv, (long)inv_raw, k->atk_inv, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv, 2 * kN - 1));
+  TRY(prepare(c, d_tsk, (long)inv_raw, k->tsk, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
 
 extern "C" int fheram_keys_prepare(fheram_ctx* c, const int64_t* atk_glwe, const int64_t* tsk,
                                    const int64_t* atk_inv, fheram_keys** out) {  // src/keys.rs:34-71
@@ -813,45 +839,21 @@ extern "C" int fheram_keys_prepare(fheram_ctx* c, const int64_t* atk_glwe, const
   const size_t atk_raw = (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n;
   const size_t inv_raw = (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n;
   int* tmp = nullptr;
-  CU(cudaMalloc(&tmp, sizeof(int) * (atk_raw * d.log_n > inv_raw ? atk_raw * d.log_n : inv_raw)));
-  CU(cudaMalloc(&k->atk, sizeof(double2) * c->atk_prep_len() * d.log_n));
-  CU(cudaMalloc(&k->atk_inv, sizeof(double2) * c->evk_inv_prep_len()));
-  CU(cudaMalloc(&k->tsk, sizeof(double2) * c->evk_inv_prep_len()));
-  TRY(upload_i64(c, atk_glwe, atk_raw * d.log_n, tmp));
-  // trace key i is stored as phi_{g_i}(key): the kernels transform phi_g(x) and get phi_g(KS(x))
-  for (int i = 0; i < d.log_n; i++)
-    TRY(prepare(c, tmp + (size_t)i * atk_raw, (long)atk_raw, k->atk + (size_t)i * c->atk_prep_len(),
-                c->atk_prep_len(), 1, d.dnum_ct, 1, d.size_evk_trace,
-                (int)((galois(d.log_n, i) + 2 * kN) % (2 * kN))));
-  CU(cudaMalloc(&k->atk7, sizeof(double2) * c->atk_prep_len() * d.log_n));
-  for (int i = 0; i < d.log_n; i++) {
-    Prep7Args pa;
-    pa.p.raw = tmp + (size_t)i * atk_raw; pa.p.out = k->atk7 + (size_t)i * c->atk_prep_len();
-    pa.p.raw_stride = (long)atk_raw; pa.p.out_stride = c->atk_prep_len();
-    pa.p.rows = d.dnum_ct; pa.p.cin = 1; pa.p.lout = d.size_evk_trace; pa.p.tw = c->tw;
-    pa.p.gal_inv = inv_mod_2n((int)((galois(d.log_n, i) + 2 * kN) % (2 * kN)));
-    pa.tw16 = c->d_tw16;
-    pa.n_polys = d.dnum_ct * 2 * d.size_evk_trace;
-    k_prepare7<<<(pa.n_polys + 1) / 2, 256, kPrep7Smem, c->stream>>>(pa);
-    c->launches++;
-    CU(cudaGetLastError());
-  }
-  CU(cudaStreamSynchronize(c->stream));
-  TRY(upload_i64(c, atk_inv, inv_raw, tmp));
-  TRY(prepare(c, tmp, (long)inv_raw, k->atk_inv, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv,
-              2 * kN - 1));
-  CU(cudaStreamSynchronize(c->stream));
-  TRY(upload_i64(c, tsk, inv_raw, tmp));
-  TRY(prepare(c, tmp, (long)inv_raw, k->tsk, c->evk_inv_prep_len(), 1, d.dnum_ggsw, 1, d.size_evk_inv));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMalloc(&tmp, sizeof(int) * (atk_raw * d.log_n + 2 * inv_raw)));
+  int *d_atk = tmp, *d_tsk = tmp + atk_raw * d.log_n, *d_inv = d_tsk + inv_raw;
+  TRY(upload_i64(c, atk_glwe, atk_raw * d.log_n, d_atk));
+  TRY(upload_i64(c, tsk, inv_raw, d_tsk));
+  TRY(upload_i64(c, atk_inv, inv_raw, d_inv));
+  TRY(keys_prepare_device(c, d_atk, d_tsk, d_inv, k));
   CU(cudaFree(tmp));
   *out = k;
   return 0;
 }
+
 extern "C" int fheram_keys_destroy(fheram_keys* k) {
   if (!k) return 0;
   cudaSetDevice(k->c->device);
-  cudaFree(k->atk); cudaFree(k->atk7); cudaFree(k->atk_inv); cudaFree(k->tsk);
+  cudaFree(k->atk); cudaFree(k->atk7); cudaFree(k->atk_inv); cudaFree(k->tsk); cudaFree(k->raw);
   delete k;
   return 0;
 }
@@ -1268,6 +1270,9 @@ struct EncBatch {
   std::vector<int8_t> pt;                // [n_glwe][N] or empty
   int pt_l = 0, pt_sh = 0;
   std::vector<int> mono;                 // [n_glwe] or empty
+  std::vector<short> poly;               // [n_poly][N] or empty (key-switching keys)
+  std::vector<int> poly_sel, sk_sel;     // [n_glwe] each, with poly
+  std::vector<int> sk_all;               // [n_sk][2 N] secrets the masks are multiplied by (empty: the caller's sk)
   std::vector<int> seq;                  // [n_glwe] position of each GLWE in its stream, or empty (= j % glwe_per_stream)
   std::vector<uint32_t> keys;            // [n_streams][8]
   std::vector<unsigned long long> word0; // [n_streams]
@@ -1377,7 +1382,7 @@ static int check_secret(const int64_t* sk, int n) {  // before any Source moves
 }
 // zero every device buffer that held secret-key material or PRNG state of an encryption call
 static void wipe_secrets(fheram_ctx* c) {
-  const int idx[] = {0, 1, 4, 5, 9, 10, 11};  // noise Source keys / positions, sk, sk spectrum, mask Source keys / positions, noise
+  const int idx[] = {0, 1, 4, 5, 9, 10, 11, 12};  // noise Source keys / positions, sk, sk spectrum, mask Source keys / positions, noise, s and s*s
   for (int i : idx)
     if (c->enc_buf[i].p) cudaMemsetAsync(c->enc_buf[i].p, 0, c->enc_buf[i].bytes, c->stream);
 }
@@ -1385,20 +1390,28 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, cons
                        int* d_out, long stride) {
   const int n = c->d.n;
   DevBuf &skraw = c->enc_buf[4], &skspec = c->enc_buf[5], &pt = c->enc_buf[6], &mono = c->enc_buf[7],
-         &seq = c->enc_buf[8], &keys = c->enc_buf[9], &word0 = c->enc_buf[10];
+         &seq = c->enc_buf[8], &keys = c->enc_buf[9], &word0 = c->enc_buf[10], &poly = c->enc_buf[12],
+         &poly_sel = c->enc_buf[13], &sk_sel = c->enc_buf[14];
   // on any failure the secret material already on the device is wiped before returning
 #define ENC_TRY(x) do { int rc_ = (x); if (rc_) { wipe_secrets(c); cudaStreamSynchronize(c->stream); return rc_; } } while (0)
 #define ENC_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { wipe_secrets(c); cudaStreamSynchronize(c->stream); return fail(FHERAM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
   {
-    std::vector<int> s32((size_t)2 * n, 0);
-    for (int i = 0; i < n; i++) s32[i] = (int)sk[i];
-    ENC_TRY(skraw.ensure(sizeof(int) * 2 * n));
-    ENC_TRY(skspec.ensure(sizeof(double2) * 2 * kM));
-    ENC_CU(cudaMemcpyAsync(skraw.p, s32.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    // the secrets the masks are multiplied by: the caller's sk, or (key generation) the n_sk output secrets of the batch
+    std::vector<int> s32;
+    if (b.sk_all.empty()) {
+      s32.assign((size_t)2 * n, 0);
+      for (int i = 0; i < n; i++) s32[i] = (int)sk[i];
+    } else {
+      s32 = b.sk_all;
+    }
+    const int n_sk = (int)(s32.size() / (2 * (size_t)n));
+    ENC_TRY(skraw.ensure(sizeof(int) * s32.size()));
+    ENC_TRY(skspec.ensure(sizeof(double2) * 2 * kM * n_sk));
+    ENC_CU(cudaMemcpyAsync(skraw.p, s32.data(), sizeof(int) * s32.size(), cudaMemcpyHostToDevice, c->stream));
     ENC_CU(cudaStreamSynchronize(c->stream));
     volatile int* vs = s32.data();  // host staging copy of the secret
-    for (int i = 0; i < 2 * n; i++) vs[i] = 0;
-    ENC_TRY(prepare(c, (const int*)skraw.p, 2 * n, (double2*)skspec.p, 2 * kM, 1, 1, 1, 1));
+    for (size_t i = 0; i < s32.size(); i++) vs[i] = 0;
+    ENC_TRY(prepare(c, (const int*)skraw.p, 2 * n, (double2*)skspec.p, 2 * kM, n_sk, 1, 1, 1));
   }
   auto up = [&](DevBuf& d, const void* h, size_t bytes) -> int {
     if (!bytes) return 0;
@@ -1411,6 +1424,9 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, cons
   ENC_TRY(up(seq, b.seq.data(), b.seq.size() * sizeof(int)));
   ENC_TRY(up(keys, b.keys.data(), b.keys.size() * sizeof(uint32_t)));
   ENC_TRY(up(word0, b.word0.data(), b.word0.size() * sizeof(unsigned long long)));
+  ENC_TRY(up(poly, b.poly.data(), b.poly.size() * sizeof(short)));
+  ENC_TRY(up(poly_sel, b.poly_sel.data(), b.poly_sel.size() * sizeof(int)));
+  ENC_TRY(up(sk_sel, b.sk_sel.data(), b.sk_sel.size() * sizeof(int)));
   EncArgs a;
   a.out = d_out; a.ct_stride = stride; a.n_glwe = b.n_glwe; a.size = b.size;
   a.nl = (b.k_noise + kK - 1) / kK - 1; a.sh = (a.nl + 1) * kK - b.k_noise;
@@ -1419,6 +1435,9 @@ static int run_encrypt(fheram_ctx* c, const int64_t* sk, const EncBatch& b, cons
   a.pt = b.pt.empty() ? nullptr : (const signed char*)pt.p;
   a.pt_l = b.pt_l; a.pt_sh = b.pt_sh;
   a.mono = b.mono.empty() ? nullptr : (const int*)mono.p;
+  a.poly = b.poly.empty() ? nullptr : (const short*)poly.p;
+  a.poly_sel = b.poly.empty() ? nullptr : (const int*)poly_sel.p;
+  a.sk_sel = b.sk_sel.empty() ? nullptr : (const int*)sk_sel.p;
   a.seq = b.seq.empty() ? nullptr : (const int*)seq.p;
   a.keys = (const uint32_t*)keys.p;
   a.word0 = (const unsigned long long*)word0.p;
@@ -1523,6 +1542,99 @@ extern "C" int fheram_address_encrypt_sk(fheram_address* a, int first, int count
     fheram_source_skip_words(xa[i], 2ull * d.size_addr * n * (n_sources == 1 ? (uint64_t)b.n_glwe : (uint64_t)per));
   a->inv_ready = false;
   return 0;
+}
+
+// EvaluationKeys::encrypt_sk (src/keys.rs:135-180) on the device, followed by EvaluationKeysPrepared::prepare: the 12
+// trace keys (GLWEAutomorphismKey, k = k_evk_trace), the GGLWE -> GGSW key and the automorphism key p = -1 (k =
+// k_evk_ggsw_inv).  The limbs of fheram_keygen from the same Sources (mask stream regenerated on the device, noise
+// sampled on the device, both Sources left where the CPU leaves them); the raw keys stay on the device next to the
+// prepared ones (fheram_keys_download_raw).
+extern "C" int fheram_keys_encrypt_sk(fheram_ctx* c, const int64_t* sk, fheram_source* xa, fheram_source* xe,
+                                      fheram_keys** out) {
+  if (!c || !sk || !xa || !xe || !out) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (xa == xe) return fail(FHERAM_ERR_INVALID, "mask and noise need distinct Sources");
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  const int n = d.n, log_n = d.log_n;
+  TRY(check_secret(sk, n));
+  const size_t atk_raw = (size_t)d.dnum_ct * 2 * d.size_evk_trace * n;
+  const size_t inv_raw = (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * n;
+  fheram_keys* k = new fheram_keys();
+  k->c = c;
+  CU(cudaMalloc(&k->raw, sizeof(int) * (atk_raw * log_n + 2 * inv_raw)));
+  int *d_atk = k->raw, *d_tsk = k->raw + atk_raw * log_n, *d_inv = d_tsk + inv_raw;
+  // phi_q(s): coefficient i of s goes to i q mod 2N with the sign of the wrap (client.cpp automorphism)
+  auto autom = [&](long q, int* o) {
+    for (int i = 0; i < n; i++) {
+      const long e = (((long)i * q) % (2L * n) + 2L * n) % (2L * n);
+      o[e % n] = e >= n ? -(int)sk[i] : (int)sk[i];
+    }
+  };
+  // plaintext polynomials: 0 = s, 1 = s * s (negacyclic, |coefficient| <= n)
+  std::vector<short> poly((size_t)2 * n, 0);
+  {
+    std::vector<long> s2(n, 0);
+    for (int i = 0; i < n; i++) {
+      if (!sk[i]) continue;
+      for (int j = 0; j < n; j++) {
+        if (!sk[j]) continue;
+        const int e = i + j;
+        s2[e % n] += (e >= n ? -1 : 1) * sk[i] * sk[j];
+      }
+    }
+    for (int i = 0; i < n; i++) { poly[i] = (short)sk[i]; poly[n + i] = (short)s2[i]; }
+  }
+  struct Part { int n_keys, rows, size, k_noise, poly; int* dst; size_t key_len; };
+  const Part parts[3] = {
+      {log_n, d.dnum_ct, d.size_evk_trace, c->params.k_evk_trace, 0, d_atk, atk_raw},       // src/keys.rs:158-165
+      {1, d.dnum_ggsw, d.size_evk_inv, c->params.k_evk_ggsw_inv, 1, d_tsk, inv_raw},          // :167-169
+      {1, d.dnum_ggsw, d.size_evk_inv, c->params.k_evk_ggsw_inv, 0, d_inv, inv_raw}};         // :171-173
+  for (int pi = 0; pi < 3; pi++) {
+    const Part& P = parts[pi];
+    EncBatch b;
+    b.n_glwe = P.n_keys * P.rows; b.size = P.size; b.k_noise = P.k_noise;
+    b.poly = poly;
+    b.sk_all.assign((size_t)P.n_keys * 2 * n, 0);
+    for (int ki = 0; ki < P.n_keys; ki++) {
+      // output secret of the key: phi_{p^-1}(s) for an automorphism key of p, s itself for the tensor key
+      long q = 1;
+      if (pi == 0) q = inv_mod_2n((int)((galois(log_n, ki) + 2 * kN) % (2 * kN)));
+      if (pi == 2) q = 2 * kN - 1;
+      autom(q, &b.sk_all[(size_t)ki * 2 * n]);
+      for (int r = 0; r < P.rows; r++) {
+        b.poly_sel.push_back(P.poly | (r << 16));
+        b.sk_sel.push_back(ki);
+      }
+    }
+    b.keys.resize(8); b.word0.resize(1);
+    fheram_source_tell(xa, b.keys.data(), (uint64_t*)&b.word0[0]);
+    b.glwe_per_stream = b.n_glwe;
+    DevBuf& d_noise = c->enc_buf[11];
+    fheram_source* xes[1] = {xe};
+    TRY(sample_noise(c, xes, 1, (size_t)b.n_glwe * n, d_noise));
+    TRY(run_encrypt(c, sk, b, d_noise, false, P.dst, (long)2 * P.size * n));
+    fheram_source_skip_words(xa, 2ull * P.size * n * (uint64_t)b.n_glwe);
+    volatile int* vs = b.sk_all.data();
+    for (size_t i = 0; i < b.sk_all.size(); i++) vs[i] = 0;
+  }
+  { volatile short* vp = poly.data(); for (size_t i = 0; i < poly.size(); i++) vp[i] = 0; }
+  TRY(keys_prepare_device(c, d_atk, d_tsk, d_inv, k));
+  *out = k;
+  return 0;
+}
+// raw limbs of keys made by fheram_keys_encrypt_sk, in the layout fheram_keygen writes (tests; a client that wants to
+// keep a copy of the public evaluation keys)
+extern "C" int fheram_keys_download_raw(fheram_keys* k, int64_t* atk_glwe, int64_t* tsk, int64_t* atk_inv) {
+  if (!k || !atk_glwe || !tsk || !atk_inv) return fail(FHERAM_ERR_INVALID, "null argument");
+  if (!k->raw) return fail(FHERAM_ERR_INVALID, "these keys were prepared from host limbs: the caller holds the raw keys");
+  fheram_ctx* c = k->c;
+  CU(cudaSetDevice(c->device));
+  const Derived& d = c->d;
+  const size_t atk_raw = (size_t)d.dnum_ct * 2 * d.size_evk_trace * d.n;
+  const size_t inv_raw = (size_t)d.dnum_ggsw * 2 * d.size_evk_inv * d.n;
+  TRY(download_i64(c, k->raw, atk_raw * d.log_n, atk_glwe));
+  TRY(download_i64(c, k->raw + atk_raw * d.log_n, inv_raw, tsk));
+  return download_i64(c, k->raw + atk_raw * d.log_n + inv_raw, inv_raw, atk_inv);
 }
 
 static int first_coord_ggsw(const Derived& d, int coord) {

@@ -19,6 +19,9 @@ struct EncArgs {
   const signed char* pt;      // dense plaintext, one signed byte per coefficient, or null
   int pt_l, pt_sh;            //   limb pt_l += v << pt_sh   (encode at k_pt, src/ram.rs:364-368)
   const int* mono;            // per GLWE monomial +/- X^pos: pos | neg << 12 | limb << 16 | col << 24, or null
+  const short* poly;          // [n_poly][N] small plaintext polynomials (key-switching keys: s, s * s), or null
+  const int* poly_sel;        // per GLWE: polynomial index | limb << 16 (added to the body as is: GGLWE row `limb`)
+  const int* sk_sel;          // per GLWE: which prepared secret (sk_spec + sk_sel[j] * 2 M) the mask is multiplied by; null: 0
   const uint32_t* keys;       // [n_streams][8] ChaCha20 keys
   const unsigned long long* word0;  // [n_streams] stream position (32-bit words) of the first mask draw
   int glwe_per_stream;        // GLWE j draws from stream j / glwe_per_stream ...
@@ -134,6 +137,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_glwe_encrypt(const EncArgs A) {
       const int mm = A.mono[j];
       m_pos = mm & 0xfff; m_val = (mm >> 12) & 1 ? -1 : 1; m_limb = (mm >> 16) & 0xff; m_col = (mm >> 24) & 1;
     }
+    const short* poly = nullptr;
+    int p_limb = -1;
+    if (A.poly) { const int ps = A.poly_sel[j]; poly = A.poly + (size_t)(ps & 0xffff) * kN; p_limb = ps >> 16; }
+    const double2* sk_spec = A.sk_spec + (A.sk_sel ? (size_t)A.sk_sel[j] * 2 * kM : 0);  // k_prepare writes two polynomials per secret
     int carry[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) carry[q] = 0;
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_glwe_encrypt(const EncArgs A) {
 #pragma unroll
       for (int jj = 0; jj < 8; jj++) {
         const double2 u = spec[256 * w + 32 * jj + lane];
-        const double2 s = __ldg(A.sk_spec + 256 * w + 32 * jj + lane);
+        const double2 s = __ldg(sk_spec + 256 * w + 32 * jj + lane);
         x[jj] = make_double2(u.x * s.x - u.y * s.y, u.x * s.y + u.y * s.x);
       }
       __syncwarp();
@@ -191,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_glwe_encrypt(const EncArgs A) {
         if (l == A.nl) t += (int)noise[i] << A.sh;
         if (pt && l == A.pt_l) t += (int)pt[i] << A.pt_sh;
         if (m_col == 0 && m_limb == l && i == m_pos) t += m_val;
+        if (poly && l == p_limb) t += (int)poly[i];
         const int dg = sext17i(t & 0x1ffff);
         carry[q] = (t - dg) >> kK;
         ob[i] = dg;

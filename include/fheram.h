@@ -298,6 +298,12 @@ int fheram_ram_encrypt_sk(fheram_ram *r, const uint8_t *data, const int64_t *sk,
 int fheram_address_encrypt_sk(fheram_address *a, int first, int count, const uint32_t *values,
                               const int64_t *sk, fheram_source *const *xa, fheram_source *const *xe,
                               int n_sources);
+/* EvaluationKeys::encrypt_sk (src/keys.rs:135-180) + EvaluationKeysPrepared::prepare (:57-71) on the device: the
+ * limbs of fheram_keygen from the same Sources, prepared and resident; fheram_keys_download_raw gives the raw keys
+ * back in fheram_keygen's layout */
+int fheram_keys_encrypt_sk(fheram_ctx *ctx, const int64_t *sk, fheram_source *xa, fheram_source *xe,
+                           fheram_keys **out);
+int fheram_keys_download_raw(fheram_keys *k, int64_t *atk_glwe, int64_t *tsk, int64_t *atk_inv);
 /* out = {noise draws sampled on the device, draws re-drawn by the host, streams sampled by the host} so far */
 int fheram_debug_encrypt_stats(fheram_ctx *ctx, uint64_t out[3]);
 

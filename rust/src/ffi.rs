@@ -36,6 +36,15 @@ extern "C" {
     pub fn fheram_keys_prepare(c: *mut fheram_ctx, atk: *const i64, tsk: *const i64, inv: *const i64,
                                out: *mut *mut fheram_keys) -> c_int;
     pub fn fheram_keys_destroy(k: *mut fheram_keys) -> c_int;
+    // EvaluationKeys::encrypt_sk + prepare on the device (colocated client / server mode), raw keys back on request
+    pub fn fheram_keys_encrypt_sk(c: *mut fheram_ctx, sk: *const i64, xa: *mut fheram_source, xe: *mut fheram_source,
+                                  out: *mut *mut fheram_keys) -> c_int;
+    pub fn fheram_keys_download_raw(k: *mut fheram_keys, atk: *mut i64, tsk: *mut i64, inv: *mut i64) -> c_int;
+    // packed host format of normalised limbs (17-bit fields)
+    pub fn fheram_pack17(limbs: *const i64, n: usize, packed: *mut u32) -> c_int;
+    pub fn fheram_unpack17(packed: *const u32, n: usize, limbs: *mut i64) -> c_int;
+    pub fn fheram_ram_read_batch_host_p17(r: *mut fheram_ram, ggsw_packed: *const u32, n: c_int, k: *const fheram_keys,
+                                          out_host: *mut i32) -> c_int;
     pub fn fheram_address_load(c: *mut fheram_ctx, ggsw: *const i64, out: *mut *mut fheram_address) -> c_int;
     pub fn fheram_address_load_batch(c: *mut fheram_ctx, ggsw: *const i64, n: c_int, out: *mut *mut fheram_address) -> c_int;
     pub fn fheram_address_destroy(a: *mut fheram_address) -> c_int;

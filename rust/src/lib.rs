@@ -96,6 +96,12 @@ pub fn gen_keys(params: &Parameters) -> (GLWESecret, EvaluationKeys) {
 pub struct EvaluationKeysPrepared(*mut fheram_keys);
 impl EvaluationKeysPrepared {
     pub fn alloc(_params: &Parameters) -> Self { EvaluationKeysPrepared(std::ptr::null_mut()) }
+    /// keygen + prepare on the device (src/keys.rs:135-180, 57-71): same limbs as `EvaluationKeys::encrypt_sk`
+    pub fn encrypt_sk_device(params: &mut Parameters, sk: &GLWESecret, xa: &mut Source, xe: &mut Source) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { fheram_keys_encrypt_sk(params.module(), sk.0.as_ptr(), xa.0, xe.0, &mut h) });
+        EvaluationKeysPrepared(h)
+    }
     pub fn prepare(&mut self, params: &mut Parameters, other: &EvaluationKeys) {
         check(unsafe { fheram_keys_prepare(params.module(), other.atk_glwe.as_ptr(),
                                            other.gglwe_to_ggsw_key.as_ptr(), other.atk_ggsw_inv.as_ptr(), &mut self.0) });

@@ -185,3 +185,35 @@ def test_streams_with_a_possible_rejection_are_sampled_by_the_host(built):
 def test_host_only_noise_mode(built):
     st = _run_noise_script({"FHERAM_ENC_NOISE": "host"})
     assert st["ok"] and st["device_draws"] == 0 and st["host_streams"] == st["streams"], st
+
+
+@pytest.mark.gpu
+def test_evaluation_keys_encrypt_sk_on_device_matches_client_side(built):
+    """EvaluationKeys::encrypt_sk (src/keys.rs:135-180) on the device: 12 trace keys, the GGLWE -> GGSW key and the
+    automorphism key p = -1, limb for limb what the CPU client side makes from the same Sources; Sources left in the
+    same state; a read with the device-made keys equals a read with the uploaded ones."""
+    import fhe_ram_b200 as fr
+    p = fr.Parameters.new(max_addr=1 << 13, word_size=1, k_pt=8)
+    sk = fr.GLWESecret.fill_ternary_prob(p, 0.5, fr.Source(0))
+    xa, xe = fr.Source(3), fr.Source(4)
+    cpu = fr.EvaluationKeys.encrypt_sk(p, sk, xa, xe)
+    ya, ye = fr.Source(3), fr.Source(4)
+    dev = fr.EvaluationKeysPrepared.encrypt_sk_gpu(p, sk, ya, ye)
+    raw = dev.download_raw()
+    assert np.array_equal(raw.atk_glwe, cpu.atk_glwe), np.count_nonzero(raw.atk_glwe != cpu.atk_glwe)
+    assert np.array_equal(raw.gglwe_to_ggsw_key, cpu.gglwe_to_ggsw_key)
+    assert np.array_equal(raw.atk_ggsw_inv, cpu.atk_ggsw_inv)
+    assert ya.position() == xa.position() and ye.position() == xe.position()
+    keys = fr.EvaluationKeysPrepared.alloc(p).prepare(cpu)
+    data = fr.Source(5).fill_bytes(1 << 13)
+    ram = fr.Ram.new(p)
+    ram.encrypt_sk(data, sk, fr.Source(11), fr.Source(12))
+    addr = fr.Address.alloc(p).encrypt_sk(p, 4242, sk, fr.Source(21), fr.Source(22))
+    a, b = ram.read(addr, keys), ram.read(addr, dev)
+    assert np.array_equal(a, b)
+    # write path (GGSW inversion keys) too
+    ram.read_prepare_write(addr, dev)
+    ram.write(np.stack([fr.encrypt_glwe(p, 99, sk)]), addr, dev)
+    v, noise = fr.decrypt_glwe(p, ram.read(addr, dev)[0], 99, sk)
+    assert v == 99 and noise < -9
+    ram.close()
