@@ -23,6 +23,7 @@
 #include "kernels_ks6.cuh"
 #include "kernels_ks7.cuh"
 #include "kernels_ext8.cuh"
+#include "kernels_ks8.cuh"
 #include "kernels_enc.cuh"
 #include "client_internal.h"
 
@@ -196,6 +197,7 @@ struct fheram_ctx {
   fheram_params params;
   Derived d;
   int device = 0, sm_count = 148;
+  int ks8_clusters = 0;  // clusters of k_ks8 (eight SMs each) that can be resident together
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
@@ -260,6 +262,7 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks7<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
   CU(cudaFuncSetAttribute(k_ext8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt8Smem));
+  CU(cudaFuncSetAttribute(k_ks8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs8Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
@@ -358,6 +361,19 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   CU(cudaMalloc(&c->d_err, sizeof(int)));
   CU(cudaMemset(c->d_err, 0, sizeof(int)));
   TRY(c->scratch.ensure((size_t)c->sm_count * 2 * c->ct_stride() * sizeof(int)));
+  {
+    // how many eight-SM clusters of k_ks8 fit at once (GPC granularity): the launch rule keeps such launches to one wave
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kKs8Cluster * 64); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = kKs8Smem;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = kKs8Cluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_ks8, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    c->ks8_clusters = n;
+  }
   *out = c;
   return 0;
 }
@@ -713,6 +729,27 @@ static int launch_ks6(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   CU(cudaGetLastError());
   return 0;
 }
+// eight-SM cluster trace kernel (kernels_ks8.cuh): FHERAM_KS8 = 0 off, 1 launches of at most one wave of clusters,
+// 2 every trace launch
+static int ks8_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FHERAM_KS8"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static int launch_ks8(fheram_ctx* c, const VmpArgs& a, int cls) {
+  if (a.n_items <= 0) return 0;
+  const int clusters = a.n_items < c->ks8_clusters ? a.n_items : c->ks8_clusters;
+  size_t e0 = 0;
+  if (c->profile) e0 = prof_event(c);
+  k_ks8<<<kKs8Cluster * clusters, 512, kKs8Smem, c->stream>>>(a, c->d_tw16);
+  if (c->profile) {
+    size_t e1 = prof_event(c);
+    c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
 // 16-point-per-thread trace kernel (kernels_ks7.cuh): FHERAM_KS7 = 0 off, 1 wide launches, 2 every launch
 static int ks7_mode() {
   static int v = -1;
@@ -1056,6 +1093,11 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     c->launches++;
     CU(cudaGetLastError());
     return 0;
+  }
+  if (c->ks8_clusters > 0 && (ks8_mode() == 2 || (ks8_mode() == 1 && n_items <= c->ks8_clusters))) {
+    VmpArgs b = a;
+    for (int s = 0; s < b.n_steps; s++) b.mat[s] = k->atk7 + (size_t)(g0 + s) * c->atk_prep_len();
+    return launch_ks8(c, b, KC_TRACE);
   }
   if (ks7_mode() == 2 || (ks7_mode() == 1 && n_items > c->sm_count)) {
     VmpArgs b = a;

@@ -25,19 +25,24 @@ SELECT = ("test_external_product_matches_oracle or test_external_product_adversa
 
 VARIANTS = {
     # word-domain key switch with in-place accumulation and two tiles in flight (k_ks4) for every key-switch launch
-    "ks4": {"FHERAM_KS3": "2", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
+    "ks4": {"FHERAM_KS3": "2", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_KS8": "0"},
     # 16-point-per-thread transform with two exchanges, two polynomials per CTA (k_ks7) for every trace chain
-    "ks7": {"FHERAM_KS7": "2"},
+    "ks7": {"FHERAM_KS7": "2", "FHERAM_KS8": "0"},
     # the same kernel for the packer's two-sided combine as well (k_ks7<MODE_COMBINE2>)
-    "ks7c": {"FHERAM_KS7": "2", "FHERAM_KS7C": "2"},
+    "ks7c": {"FHERAM_KS7": "2", "FHERAM_KS7C": "2", "FHERAM_KS8": "0"},
     # one operation per SM, 512 threads, tiles parked in tensor memory (k_ks5), trace and combine
-    "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0", "FHERAM_KS7": "0"},
+    "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0", "FHERAM_KS7": "0", "FHERAM_KS8": "0"},
+    # the two-SM cluster kernel (k_ks6) for every narrow trace chain (the default hands the narrowest ones to k_ks8)
+    "ks6": {"FHERAM_KS8": "0"},
+    # one trace chain per cluster of eight SMs, words exchanged through L2 (k_ks8), for every trace launch
+    "ks8": {"FHERAM_KS8": "2"},
     # column-split k_vmp for every narrow key switch (two CTAs per operation, one launch per chain step)
-    "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0"},
+    "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_KS8": "0"},
     # round-1 external-product kernels (k_ext3 forced for every launch, GGSWs prepared in its frequency order)
-    "ext3": {"FHERAM_EXT8": "0", "FHERAM_KS3": "2"},
+    "ext3": {"FHERAM_EXT8": "0", "FHERAM_KS3": "2", "FHERAM_KS8": "0"},
     # round-1 narrow external product (column-split k_vmp<EXT>) and the single-CTA k_vmp without column split
-    "ext_vmp": {"FHERAM_EXT8": "0", "FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_SPLIT": "0"},
+    "ext_vmp": {"FHERAM_EXT8": "0", "FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_SPLIT": "0",
+                "FHERAM_KS8": "0"},
 }
 
 
