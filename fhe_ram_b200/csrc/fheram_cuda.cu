@@ -197,7 +197,7 @@ struct fheram_ctx {
   fheram_params params;
   Derived d;
   int device = 0, sm_count = 148;
-  int ks8_clusters = 0;  // clusters of k_ks8 (eight SMs each) that can be resident together
+  int ks8_clusters[2] = {0, 0};  // clusters of k_ks8 that can be resident together: [0] eight SMs each, [1] four
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
@@ -262,7 +262,10 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks7<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
   CU(cudaFuncSetAttribute(k_ext8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt8Smem));
-  CU(cudaFuncSetAttribute(k_ks8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs8Smem));
+  CU(cudaFuncSetAttribute(k_ks8<8, MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(8)));
+  CU(cudaFuncSetAttribute(k_ks8<8, MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(8)));
+  CU(cudaFuncSetAttribute(k_ks8<4, MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(4)));
+  CU(cudaFuncSetAttribute(k_ks8<4, MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(4)));
   CU(cudaFuncSetAttribute(k_ks6<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks6<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
   CU(cudaFuncSetAttribute(k_ks5<MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs5Smem));
@@ -361,18 +364,22 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
   CU(cudaMalloc(&c->d_err, sizeof(int)));
   CU(cudaMemset(c->d_err, 0, sizeof(int)));
   TRY(c->scratch.ensure((size_t)c->sm_count * 2 * c->ct_stride() * sizeof(int)));
-  {
-    // how many eight-SM clusters of k_ks8 fit at once (GPC granularity): the launch rule keeps such launches to one wave
+  for (int v = 0; v < 2; v++) {
+    // how many clusters of k_ks8 fit at once (GPC granularity): the launch rule keeps such launches to one wave
+    const int cl = v == 0 ? 8 : 4;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(kKs8Cluster * 64); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = kKs8Smem;
+    cfg.gridDim = dim3(cl * 64); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = ks8_smem(cl);
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension;
-    at.val.clusterDim.x = kKs8Cluster; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    at.val.clusterDim.x = cl; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_ks8, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
-    c->ks8_clusters = n;
+    const cudaError_t e = v == 0 ? cudaOccupancyMaxActiveClusters(&n, k_ks8<8, MODE_TRACE>, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(&n, k_ks8<4, MODE_TRACE>, &cfg);
+    if (e != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    const int cap = (int)(c->scratch.bytes / (kKs8ScratchWords * sizeof(unsigned long long)));
+    c->ks8_clusters[v] = n < cap ? n : cap;
   }
   *out = c;
   return 0;
@@ -729,19 +736,31 @@ static int launch_ks6(fheram_ctx* c, K kernel, const VmpArgs& a, int cls) {
   CU(cudaGetLastError());
   return 0;
 }
-// eight-SM cluster trace kernel (kernels_ks8.cuh): FHERAM_KS8 = 0 off, 1 launches of at most one wave of clusters,
-// 2 every trace launch
+// cluster key-switch kernels (kernels_ks8.cuh, eight or four SMs per chain): FHERAM_KS8 = 0 off, 1 launches of at
+// most one wave of clusters, 2 every trace / combine launch, 3 the same with four-SM clusters only
 static int ks8_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FHERAM_KS8"); v = e ? atoi(e) : 1; }
   return v;
 }
-static int launch_ks8(fheram_ctx* c, const VmpArgs& a, int cls) {
+// cluster variant for n_items key switches: 0 = eight SMs per chain, 1 = four, -1 = not a k_ks8 launch
+static int ks8_variant(const fheram_ctx* c, int n_items) {
+  if (ks8_mode() == 0) return -1;
+  if (ks8_mode() == 3) return c->ks8_clusters[1] > 0 ? 1 : -1;  // four-SM clusters for every launch (tests)
+  if (c->ks8_clusters[0] > 0 && n_items <= c->ks8_clusters[0]) return 0;
+  if (c->ks8_clusters[1] > 0 && n_items <= c->ks8_clusters[1]) return 1;
+  if (ks8_mode() == 2) return c->ks8_clusters[1] > 0 ? 1 : (c->ks8_clusters[0] > 0 ? 0 : -1);
+  return -1;
+}
+template <int MODE>
+static int launch_ks8(fheram_ctx* c, int variant, const VmpArgs& a, int cls) {
   if (a.n_items <= 0) return 0;
-  const int clusters = a.n_items < c->ks8_clusters ? a.n_items : c->ks8_clusters;
+  const int cl = variant == 0 ? 8 : 4, cap = c->ks8_clusters[variant];
+  const int clusters = a.n_items < cap ? a.n_items : cap;
   size_t e0 = 0;
   if (c->profile) e0 = prof_event(c);
-  k_ks8<<<kKs8Cluster * clusters, 512, kKs8Smem, c->stream>>>(a, c->d_tw16);
+  if (variant == 0) k_ks8<8, MODE><<<cl * clusters, 512, ks8_smem(8), c->stream>>>(a, c->d_tw16);
+  else k_ks8<4, MODE><<<cl * clusters, 512, ks8_smem(4), c->stream>>>(a, c->d_tw16);
   if (c->profile) {
     size_t e1 = prof_event(c);
     c->ev_recs.push_back({cls, e0, e1, (uint64_t)a.n_items, (uint64_t)a.n_steps});
@@ -1094,10 +1113,10 @@ static int run_trace_chain(fheram_ctx* c, const fheram_keys* k, int n_items, con
     CU(cudaGetLastError());
     return 0;
   }
-  if (c->ks8_clusters > 0 && (ks8_mode() == 2 || (ks8_mode() == 1 && n_items <= c->ks8_clusters))) {
+  if (const int v8 = ks8_variant(c, n_items); v8 >= 0) {
     VmpArgs b = a;
     for (int s = 0; s < b.n_steps; s++) b.mat[s] = k->atk7 + (size_t)(g0 + s) * c->atk_prep_len();
-    return launch_ks8(c, b, KC_TRACE);
+    return launch_ks8<MODE_TRACE>(c, v8, b, KC_TRACE);
   }
   if (ks7_mode() == 2 || (ks7_mode() == 1 && n_items > c->sm_count)) {
     VmpArgs b = a;
@@ -1139,6 +1158,11 @@ static int run_combine2(fheram_ctx* c, const fheram_keys* k, int n_items, const 
   a.gal[0] = (int)((galois(c->d.log_n, level) + 2 * kN) % (2 * kN));
   a.gal_inv[0] = inv_mod_2n(a.gal[0]);
   a.rot_const = 1 << (c->d.log_n - level - 1);  // t
+  if (const int v8 = ks8_variant(c, n_items); v8 >= 0) {
+    VmpArgs b = a;
+    b.mat[0] = k->atk7 + (size_t)level * c->atk_prep_len();
+    return launch_ks8<MODE_COMBINE2>(c, v8, b, KC_COMBINE2);
+  }
   {
     static int ks7c = -1;  // two-sided combine on k_ks7: FHERAM_KS7C = 0 off, 1 wide launches, 2 every launch
     if (ks7c < 0) { const char* e = getenv("FHERAM_KS7C"); ks7c = e ? atoi(e) : 0; }

@@ -34,8 +34,11 @@ VARIANTS = {
     "ks5": {"FHERAM_KS5": "2", "FHERAM_KS6": "0", "FHERAM_KS7": "0", "FHERAM_KS8": "0"},
     # the two-SM cluster kernel (k_ks6) for every narrow trace chain (the default hands the narrowest ones to k_ks8)
     "ks6": {"FHERAM_KS8": "0"},
-    # one trace chain per cluster of eight SMs, words exchanged through L2 (k_ks8), for every trace launch
+    # one key-switch chain per cluster of eight (or, beyond one wave of those, four) SMs, contributions exchanged
+    # through L2 (k_ks8), for every trace / combine launch
     "ks8": {"FHERAM_KS8": "2"},
+    # the four-SM cluster variant of k_ks8 (two output polynomials per CTA) for every trace / combine launch
+    "ks8c4": {"FHERAM_KS8": "3"},
     # column-split k_vmp for every narrow key switch (two CTAs per operation, one launch per chain step)
     "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_KS8": "0"},
     # round-1 external-product kernels (k_ext3 forced for every launch, GGSWs prepared in its frequency order)
