@@ -24,6 +24,7 @@
 #include "kernels_ks7.cuh"
 #include "kernels_ext8.cuh"
 #include "kernels_ks8.cuh"
+#include "kernels_ext9.cuh"
 #include "kernels_enc.cuh"
 #include "client_internal.h"
 
@@ -197,6 +198,7 @@ struct fheram_ctx {
   fheram_params params;
   Derived d;
   int device = 0, sm_count = 148;
+  int ext9_clusters[2] = {0, 0}; // the same for k_ext9
   int ks8_clusters[2] = {0, 0};  // clusters of k_ks8 that can be resident together: [0] eight SMs each, [1] four
   cudaStream_t stream = nullptr;
   bool own_stream = true;
@@ -262,6 +264,8 @@ static int set_attrs() {
   CU(cudaFuncSetAttribute(k_ks7<MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKs7Smem));
   CU(cudaFuncSetAttribute(k_prepare7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrep7Smem));
   CU(cudaFuncSetAttribute(k_ext8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExt8Smem));
+  CU(cudaFuncSetAttribute(k_ext9<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext9_smem(8)));
+  CU(cudaFuncSetAttribute(k_ext9<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext9_smem(4)));
   CU(cudaFuncSetAttribute(k_ks8<8, MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(8)));
   CU(cudaFuncSetAttribute(k_ks8<8, MODE_COMBINE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(8)));
   CU(cudaFuncSetAttribute(k_ks8<4, MODE_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks8_smem(4)));
@@ -380,6 +384,12 @@ extern "C" int fheram_ctx_create(const fheram_params* p, int device, fheram_ctx*
     if (e != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
     const int cap = (int)(c->scratch.bytes / (kKs8ScratchWords * sizeof(unsigned long long)));
     c->ks8_clusters[v] = n < cap ? n : cap;
+    cfg.dynamicSmemBytes = ext9_smem(cl);
+    n = 0;
+    const cudaError_t e2 = v == 0 ? cudaOccupancyMaxActiveClusters(&n, k_ext9<8>, &cfg)
+                                  : cudaOccupancyMaxActiveClusters(&n, k_ext9<4>, &cfg);
+    if (e2 != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    c->ext9_clusters[v] = n < cap ? n : cap;
   }
   *out = c;
   return 0;
@@ -1054,6 +1064,31 @@ static int run_ext_chain(fheram_ctx* c, int n_items, const int* src, const int* 
   a.mat_div = mat_div; a.mat_stride = mat_stride;
   if (ext8_mode() != 0) {
     if (n_items <= 0) return 0;
+    // launches of at most one wave of clusters: one chain per cluster of eight (four) SMs (kernels_ext9.cuh);
+    // FHERAM_EXT9 = 0 off, 1 default, 2 every launch, 3 every launch on four-SM clusters
+    static int ext9 = -1;
+    if (ext9 < 0) { const char* e = getenv("FHERAM_EXT9"); ext9 = e ? atoi(e) : 1; }
+    int v9 = -1;
+    if (ext9 == 3) v9 = c->ext9_clusters[1] > 0 ? 1 : -1;
+    else if (ext9 >= 1) {
+      if (c->ext9_clusters[0] > 0 && n_items <= c->ext9_clusters[0]) v9 = 0;
+      else if (c->ext9_clusters[1] > 0 && (n_items <= c->ext9_clusters[1] || ext9 == 2)) v9 = 1;
+    }
+    if (v9 >= 0) {
+      const int cl = v9 == 0 ? 8 : 4, cap = c->ext9_clusters[v9];
+      const int clusters = n_items < cap ? n_items : cap;
+      size_t e0 = 0;
+      if (c->profile) e0 = prof_event(c);
+      if (v9 == 0) k_ext9<8><<<cl * clusters, 512, ext9_smem(8), c->stream>>>(a, c->d_tw16);
+      else k_ext9<4><<<cl * clusters, 512, ext9_smem(4), c->stream>>>(a, c->d_tw16);
+      if (c->profile) {
+        size_t e1 = prof_event(c);
+        c->ev_recs.push_back({KC_EXT, e0, e1, (uint64_t)n_items, (uint64_t)n_dig});
+      }
+      c->launches++;
+      CU(cudaGetLastError());
+      return 0;
+    }
     const int grid = n_items < c->sm_count ? n_items : c->sm_count;
     size_t e0 = 0;
     if (c->profile) e0 = prof_event(c);

@@ -41,6 +41,11 @@ VARIANTS = {
     "ks8c4": {"FHERAM_KS8": "3"},
     # column-split k_vmp for every narrow key switch (two CTAs per operation, one launch per chain step)
     "vmp_split": {"FHERAM_KS3": "0", "FHERAM_KS5": "0", "FHERAM_KS7": "0", "FHERAM_KS8": "0"},
+    # one-SM-per-ciphertext external product (k_ext8) for the narrow launches too (the default hands them to k_ext9)
+    "ext8": {"FHERAM_EXT9": "0"},
+    # one external-product chain per cluster of eight / four SMs (k_ext9) for every launch
+    "ext9": {"FHERAM_EXT9": "2"},
+    "ext9c4": {"FHERAM_EXT9": "3"},
     # round-1 external-product kernels (k_ext3 forced for every launch, GGSWs prepared in its frequency order)
     "ext3": {"FHERAM_EXT8": "0", "FHERAM_KS3": "2", "FHERAM_KS8": "0"},
     # round-1 narrow external product (column-split k_vmp<EXT>) and the single-CTA k_vmp without column split
