@@ -194,6 +194,7 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+constexpr size_t kSmallDownload = (size_t)1 << 19;  // limbs (2 MiB of int32): up to 21 GLWEs at N = 4096, k = 51
 struct fheram_ctx {
   fheram_params params;
   Derived d;
@@ -203,6 +204,11 @@ struct fheram_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;  // uploads of the asynchronous address path
+  // side stream of read_prepare_write: the inverse address of the write that follows (prepare_inv) is built beside
+  // the read instead of behind it; its kernels take their per-CTA scratch from scratch_side
+  cudaStream_t side = nullptr;
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  bool on_side = false;
   // multi-GPU: one context per rank, NCCL communicator over NVLink (fheram_comm_init)
   ncclComm_t comm = nullptr;
   ncclComm_t comm_prep = nullptr;  // second communicator: all-gather of prepared GGSWs on the upload stream, beside the reads
@@ -214,6 +220,8 @@ struct fheram_ctx {
   uint64_t launches = 0;
   DevBuf stage64;   // int64 staging for uploads / downloads
   DevBuf scratch;   // per-CTA scratch of the vmp kernels
+  DevBuf scratch_side;
+  int* pin32 = nullptr;  // pinned host buffer of small downloads (download_i64)
   DevBuf enc_buf[15];  // operands of the encryption kernels, kept between calls (cudaFree synchronizes the device)
   uint64_t enc_stats[3] = {0, 0, 0};  // noise draws sampled on the device / patched by the host / streams resampled on the host
   DevBuf opbuf[3];  // op-level entry points
@@ -409,6 +417,12 @@ extern "C" int fheram_ctx_destroy(fheram_ctx* c) {
   for (auto& b : c->enc_buf) b.release();
   cudaFree(c->d_tw); cudaFree(c->d_tw16); cudaFree(c->d_err);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->side) {
+    cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side);
+    cudaEventDestroy(c->side_fork); cudaEventDestroy(c->side_join);
+  }
+  c->scratch_side.release();
+  if (c->pin32) cudaFreeHost(c->pin32);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -614,6 +628,16 @@ static int upload_i64(fheram_ctx* c, const int64_t* h, size_t n, int* d_out) {
   return 0;
 }
 static int download_i64(fheram_ctx* c, const int* d_in, size_t n, int64_t* h) {
+  if (n <= kSmallDownload) {
+    // results of single operations (word_size GLWEs): int32 limbs by DMA into a pinned buffer of the context, widened by
+    // the host -- half the bytes over PCIe, no conversion kernel, no staging copy out of pageable memory by the driver
+    if (!c->pin32) CU(cudaMallocHost(&c->pin32, kSmallDownload * sizeof(int)));
+    CU(cudaMemcpyAsync(c->pin32, d_in, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int* p = c->pin32;
+    for (size_t i = 0; i < n; i++) h[i] = p[i];
+    return 0;
+  }
   const size_t chunk = (size_t)64 << 20;
   for (size_t off = 0; off < n; off += chunk) {
     size_t m = n - off < chunk ? n - off : chunk;
@@ -639,7 +663,7 @@ static VmpArgs base_args(fheram_ctx* c, int n_items, const int* src, int* dst, l
   a.n_items = n_items;
   a.src = src; a.dst = dst;
   a.ct_stride = ct_stride;
-  a.scratch = (int*)c->scratch.p;
+  a.scratch = (int*)(c->on_side ? c->scratch_side.p : c->scratch.p);
   a.sign = 1;
   for (int i = 0; i < kMaxSteps; i++) { a.gal[i] = 1; a.gal_inv[i] = 1; }
   a.tw = c->tw;
@@ -2195,6 +2219,32 @@ extern "C" int fheram_ram_read_prepare_write(fheram_ram* r, const fheram_address
   if (r && r->n_shards != 1 && !comm_matches(r->c, r->shard, r->n_shards))
     return fail(FHERAM_ERR_INVALID, "sharded RAM: call fheram_comm_init first, or use rpw_local_device / rpw_finish_device");
   const int32_t *part = nullptr, *res = nullptr;
+  if (!r || !addr || !k) return fail(FHERAM_ERR_INVALID, "null argument");
+  // the inverse address the write that follows needs (src/ram.rs:260-271,278-289) depends on the address and the keys
+  // only: it is built on a side stream beside the read (18 CTAs of key switches + vmp_prepare next to launches that
+  // leave most SMs idle in their narrow phases) and joined before this call's last operation
+  fheram_ctx* cx = r->c;
+  bool forked = false;
+  if (addr->c == cx && k->c == cx && addr->count == 1 && !addr->inv_ready && r->loaded && !r->state && !r->rotated) {
+    CU(cudaSetDevice(cx->device));
+    if (!cx->side) {
+      CU(cudaStreamCreateWithFlags(&cx->side, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&cx->side_fork, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&cx->side_join, cudaEventDisableTiming));
+    }
+    const Derived& dd = cx->d;
+    TRY(cx->scratch_side.ensure(sizeof(int) * (size_t)dd.n_ggsw * dd.dnum_ct * 8 * dd.size_addr * dd.n));
+    CU(cudaEventRecord(cx->side_fork, cx->stream));
+    CU(cudaStreamWaitEvent(cx->side, cx->side_fork, 0));
+    cudaStream_t main_stream = cx->stream;
+    cx->stream = cx->side; cx->on_side = true;
+    const int rc = address_prepare_inv(addr, k);
+    cx->stream = main_stream; cx->on_side = false;
+    CU(cudaEventRecord(cx->side_join, cx->side));
+    forked = true;
+    if (rc) { cudaStreamWaitEvent(cx->stream, cx->side_join, 0); return rc; }
+  }
+  const int rc_body = [&]() -> int {
   TRY(fheram_ram_rpw_local_device(r, addr, k, &part));
   if (r->n_shards != 1) {
     // every rank needs tree[0][0] (Ram::write then runs without communication): all-gather the packed partials and
@@ -2207,9 +2257,11 @@ extern "C" int fheram_ram_read_prepare_write(fheram_ram* r, const fheram_address
   }
   TRY(fheram_ram_rpw_finish_device(r, part, addr, k, &res));
   TRY(download_i64(r->c, res, (size_t)r->c->params.word_size * r->c->ct_stride(), out));
-  // the inverse address the write that follows needs (src/ram.rs:260-271,278-289) is queued now, behind the
-  // downloaded result: it runs while the host works on the word to write instead of at the head of Ram::write
-  return address_prepare_inv(addr, k);
+  return 0;
+  }();
+  if (forked) CU(cudaStreamWaitEvent(cx->stream, cx->side_join, 0));  // whatever follows on the RAM sees the inverse address
+  if (rc_body) return rc_body;
+  return address_prepare_inv(addr, k);  // (already done on the side stream unless the fork was skipped)
 }
 
 // CoordinatePrepared::prepare_inv for every coordinate of the address (src/ram.rs:260-271,
