@@ -22,9 +22,15 @@ limbs = addrs.download_raw().reshape(B, -1)
 ram.read_batch_host_p17(api.pack17(limbs[:16]), 16, keys)           # k_unpack17 (+ the pipeline)
 ram.read_batch_host(limbs[:16], 16, keys)                           # k_i64_to_i32, k_i32_to_i64
 one = fr.Address.from_limbs(p, limbs[0], 1)
-ram.read(one, keys)                                                 # narrow: k_ext8 on 4 items, k_ks6, k_ks5
+ram.read(one, keys)                                                 # narrow: k_ext9<8>, k_ks8<8, ...>, k_ks6, k_ks5
 ram.read_prepare_write(one, keys)
 w = np.stack([fr.encrypt_glwe(p, v, sk) for v in (1, 2, 3, 4)])
 ram.write(w, one, keys)                                             # k_vmp<AUTO / EXPAND> (GGSW inversion), k_sub_add_normalize, k_rotate
+# launch shapes of a RAM sharded over 8 GPUs (32 ciphertexts per rank): the four-SM cluster variants k_ks8<4, ...>, k_ext9<4>
+rng = np.random.default_rng(0)
+cts32 = rng.integers(-(1 << 16), 1 << 16, size=(32, p.glwe_len()), dtype=np.int64)
+api.glwe_trace(p, keys, cts32)
+api.glwe_pack(p, keys, cts32)
+api.coordinate_product(p, cts32, limbs[0][: 4 * p.ggsw_len()], 4)
 p.synchronize()
 print("done", p.launch_count(), "launches")
