@@ -367,6 +367,9 @@ static void tf_free(orc_ctx *c) { free(c->tw_re); free(c->tw_im); }
 #else
 #define ORC_CLONES
 #endif
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
 #define ORC_MAGIC 6755399441055744.0 /* 2^52 + 2^51 */
 static inline double i64_to_f64(i64 v) {
   union { double d; i64 i; } u;
@@ -401,8 +404,11 @@ static void tf_forward(const orc_ctx *c, const i64 *a, tfe *out, int mont) {
       const double w1r = c->tw_re[s + b], w1i = c->tw_im[s + b];
       const double w2r = c->tw_re[2 * s + 2 * b], w2i = c->tw_im[2 * s + 2 * b];
       const double w3r = c->tw_re[2 * s + 2 * b + 1], w3i = c->tw_im[2 * s + 2 * b + 1];
-      double *r0 = re + (size_t)b * t, *i0 = im + (size_t)b * t;
-      double *r1 = r0 + q, *i1 = i0 + q, *r2 = r0 + 2 * q, *i2 = i0 + 2 * q, *r3 = r0 + 3 * q, *i3 = i0 + 3 * q;
+      /* the quarters do not overlap: without restrict + ivdep gcc leaves this loop scalar */
+      double *restrict r0 = re + (size_t)b * t, *restrict i0 = im + (size_t)b * t;
+      double *restrict r1 = r0 + q, *restrict i1 = i0 + q, *restrict r2 = r0 + 2 * q, *restrict i2 = i0 + 2 * q,
+             *restrict r3 = r0 + 3 * q, *restrict i3 = i0 + 3 * q;
+#pragma GCC ivdep
       for (int j = 0; j < q; j++) {
         /* stage s: (0,2) and (1,3) with w1 */
         double ar = r2[j] * w1r - i2[j] * w1i, ai = r2[j] * w1i + i2[j] * w1r;
@@ -418,6 +424,52 @@ static void tf_forward(const orc_ctx *c, const i64 *a, tfe *out, int mont) {
     }
     t = q;
   }
+#ifdef __AVX2__
+  if (t == 8 && s * 8 == m) {
+    /* last three stages (distances 4, 2, 1) in registers, one block of 8 points per iteration */
+    const __m256d sg2 = _mm256_set_pd(-1.0, -1.0, 1.0, 1.0), sg1 = _mm256_set_pd(-1.0, 1.0, -1.0, 1.0);
+    const double *w4r = c->tw_re + s, *w4i = c->tw_im + s;          /* stage s: one twiddle per block */
+    const double *w2r = c->tw_re + 2 * s, *w2i = c->tw_im + 2 * s;  /* stage 2s: one per half block */
+    const double *w1r = c->tw_re + 4 * s, *w1i = c->tw_im + 4 * s;  /* stage 4s: one per pair */
+    for (int b = 0; b < s; b++) {
+      __m256d r0 = _mm256_loadu_pd(re + 8 * b), r1 = _mm256_loadu_pd(re + 8 * b + 4);
+      __m256d i0 = _mm256_loadu_pd(im + 8 * b), i1 = _mm256_loadu_pd(im + 8 * b + 4);
+      { /* distance 4 */
+        const __m256d wr = _mm256_broadcast_sd(w4r + b), wi = _mm256_broadcast_sd(w4i + b);
+        const __m256d vr = _mm256_fnmadd_pd(i1, wi, _mm256_mul_pd(r1, wr));
+        const __m256d vi = _mm256_fmadd_pd(i1, wr, _mm256_mul_pd(r1, wi));
+        r1 = _mm256_sub_pd(r0, vr); r0 = _mm256_add_pd(r0, vr);
+        i1 = _mm256_sub_pd(i0, vi); i0 = _mm256_add_pd(i0, vi);
+      }
+#define ORC_FWD_D2(R, I, K)                                                                                     \
+      {                                                                                                         \
+        const __m256d wr = _mm256_broadcast_sd(w2r + 2 * b + (K)), wi = _mm256_broadcast_sd(w2i + 2 * b + (K)); \
+        const __m256d ur = _mm256_permute2f128_pd(R, R, 0x00), yr = _mm256_permute2f128_pd(R, R, 0x11);         \
+        const __m256d ui = _mm256_permute2f128_pd(I, I, 0x00), yi = _mm256_permute2f128_pd(I, I, 0x11);         \
+        const __m256d vr = _mm256_fnmadd_pd(yi, wi, _mm256_mul_pd(yr, wr));                                     \
+        const __m256d vi = _mm256_fmadd_pd(yi, wr, _mm256_mul_pd(yr, wi));                                      \
+        R = _mm256_fmadd_pd(vr, sg2, ur); I = _mm256_fmadd_pd(vi, sg2, ui);                                     \
+      }
+      ORC_FWD_D2(r0, i0, 0)
+      ORC_FWD_D2(r1, i1, 1)
+#define ORC_FWD_D1(R, I, K)                                                                                          \
+      {                                                                                                              \
+        const __m256d wr = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1r + 4 * b + 2 * (K))), 0x50); \
+        const __m256d wi = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1i + 4 * b + 2 * (K))), 0x50); \
+        const __m256d ur = _mm256_permute_pd(R, 0x0), yr = _mm256_permute_pd(R, 0xF);                                \
+        const __m256d ui = _mm256_permute_pd(I, 0x0), yi = _mm256_permute_pd(I, 0xF);                                \
+        const __m256d vr = _mm256_fnmadd_pd(yi, wi, _mm256_mul_pd(yr, wr));                                          \
+        const __m256d vi = _mm256_fmadd_pd(yi, wr, _mm256_mul_pd(yr, wi));                                           \
+        R = _mm256_fmadd_pd(vr, sg1, ur); I = _mm256_fmadd_pd(vi, sg1, ui);                                          \
+      }
+      ORC_FWD_D1(r0, i0, 0)
+      ORC_FWD_D1(r1, i1, 1)
+      _mm256_storeu_pd(re + 8 * b, r0); _mm256_storeu_pd(re + 8 * b + 4, r1);
+      _mm256_storeu_pd(im + 8 * b, i0); _mm256_storeu_pd(im + 8 * b + 4, i1);
+    }
+    return;
+  }
+#endif
   /* remaining single stages */
   for (; s < m; s <<= 1) {
     t >>= 1;
@@ -453,6 +505,39 @@ static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
   const int m = c->n / 2;
   double *re = a, *im = a + m;
   int t = 1, s = m >> 1;
+#ifdef __AVX2__
+  if (m >= 8) {
+    /* first two stages (distances 1 and 2) in registers, four points per vector */
+    const double *w1r = c->tw_re + s, *w1i = c->tw_im + s;          /* one twiddle per pair */
+    const double *w2r = c->tw_re + s / 2, *w2i = c->tw_im + s / 2;  /* one per block of four */
+    for (int b = 0; b < m / 4; b++) {
+      __m256d R = _mm256_loadu_pd(re + 4 * b), I = _mm256_loadu_pd(im + 4 * b);
+      { /* distance 1: (x, y) <- (x + y, (x - y) conj(w)) */
+        const __m256d wr = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1r + 2 * b)), 0x50);
+        const __m256d wi = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1i + 2 * b)), 0x50);
+        const __m256d ur = _mm256_permute_pd(R, 0x0), yr = _mm256_permute_pd(R, 0xF);
+        const __m256d ui = _mm256_permute_pd(I, 0x0), yi = _mm256_permute_pd(I, 0xF);
+        const __m256d sr = _mm256_add_pd(ur, yr), si = _mm256_add_pd(ui, yi);
+        const __m256d dr = _mm256_sub_pd(ur, yr), di = _mm256_sub_pd(ui, yi);
+        const __m256d pr = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));   /* dr wr + di wi */
+        const __m256d pi = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr));  /* di wr - dr wi */
+        R = _mm256_blend_pd(sr, pr, 0xA); I = _mm256_blend_pd(si, pi, 0xA);
+      }
+      { /* distance 2 */
+        const __m256d wr = _mm256_broadcast_sd(w2r + b), wi = _mm256_broadcast_sd(w2i + b);
+        const __m256d ur = _mm256_permute2f128_pd(R, R, 0x00), yr = _mm256_permute2f128_pd(R, R, 0x11);
+        const __m256d ui = _mm256_permute2f128_pd(I, I, 0x00), yi = _mm256_permute2f128_pd(I, I, 0x11);
+        const __m256d sr = _mm256_add_pd(ur, yr), si = _mm256_add_pd(ui, yi);
+        const __m256d dr = _mm256_sub_pd(ur, yr), di = _mm256_sub_pd(ui, yi);
+        const __m256d pr = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));
+        const __m256d pi = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr));
+        R = _mm256_blend_pd(sr, pr, 0xC); I = _mm256_blend_pd(si, pi, 0xC);
+      }
+      _mm256_storeu_pd(re + 4 * b, R); _mm256_storeu_pd(im + 4 * b, I);
+    }
+    t = 4; s >>= 2;
+  }
+#endif
   /* single stages while the distance is below 4 */
   for (; s >= 1 && t < 4; s >>= 1) {
     for (int b = 0; b < s; b++) {
@@ -474,8 +559,10 @@ static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
       const double w2r = c->tw_re[s + 2 * b], w2i = -c->tw_im[s + 2 * b];
       const double w3r = c->tw_re[s + 2 * b + 1], w3i = -c->tw_im[s + 2 * b + 1];
       const double w1r = c->tw_re[h + b], w1i = -c->tw_im[h + b];
-      double *r0 = re + (size_t)b * 4 * t, *i0 = im + (size_t)b * 4 * t;
-      double *r1 = r0 + t, *i1 = i0 + t, *r2 = r0 + 2 * t, *i2 = i0 + 2 * t, *r3 = r0 + 3 * t, *i3 = i0 + 3 * t;
+      double *restrict r0 = re + (size_t)b * 4 * t, *restrict i0 = im + (size_t)b * 4 * t;
+      double *restrict r1 = r0 + t, *restrict i1 = i0 + t, *restrict r2 = r0 + 2 * t, *restrict i2 = i0 + 2 * t,
+             *restrict r3 = r0 + 3 * t, *restrict i3 = i0 + 3 * t;
+#pragma GCC ivdep
       for (int j = 0; j < t; j++) {
         /* stage s: (0,1) with w2, (2,3) with w3 */
         double x0r = r0[j] + r1[j], x0i = i0[j] + i1[j], d0r = r0[j] - r1[j], d0i = i0[j] - i1[j];
@@ -579,6 +666,16 @@ static void count_op(const orc_ctx *c, int which) {
 
 static inline i64 get_digit(int k, i64 x) { return (i64)((u64)x << (64 - k)) >> (64 - k); }
 static inline i64 get_carry(int k, i64 x, i64 d) { return (x - d) >> k; }
+/* the same two functions with logical shifts only, so that gcc vectorises the loops below for AVX2 (no 64-bit
+ * arithmetic right shift there): balanced digit = ((x + 2^(k-1)) mod 2^k) - 2^(k-1); x - d is a multiple of 2^k and
+ * |x - d| < 2^62 for every value on the path (limbs and their sums stay below 2^52) */
+static inline i64 digit_l(int k, i64 x) {
+  const u64 h = (u64)1 << (k - 1), mask = ((u64)1 << k) - 1;
+  return (i64)((((u64)x + h) & mask) - h);
+}
+static inline i64 carry_l(int k, i64 x, i64 d) {
+  return (i64)((((u64)(x - d) + ((u64)1 << 62)) >> k) - ((u64)1 << (62 - k)));
+}
 
 /* Poulpy [spec] vec_znx_normalize / vec_znx_big_normalize, same base2k on both sides.
  * Walks limbs from least to most significant; limbs of `a` beyond res_size contribute their
@@ -587,15 +684,35 @@ static inline i64 get_carry(int k, i64 x, i64 d) { return (x - d) >> k; }
  * here exactly: digit(digit(x)+c) = digit(x+c) and the carries sum to (x+c-digit)>>k. */
 static void vz_normalize(int n, int k, i64 *res, int rcols, int rcol, int rsize, const i64 *a,
                          int acols, int acol, int asize) {
-  for (int i = 0; i < n; i++) {
-    i64 c = 0;
-    for (int j = asize - 1; j >= 0; j--) {
-      i64 t = AT(a, acols, n, acol, j)[i] + c;
-      i64 d = get_digit(k, t);
-      c = get_carry(k, t, d);
-      if (j < rsize) AT(res, rcols, n, rcol, j)[i] = d;
+  /* limb by limb over all coefficients (the carries of one limb in an array): same integers as the
+   * coefficient-by-coefficient walk, written so that the inner loops vectorise */
+  i64 *restrict cy = (i64 *)malloc(sizeof(i64) * (size_t)n);
+  memset(cy, 0, sizeof(i64) * (size_t)n);
+  for (int j = asize - 1; j >= 0; j--) {
+    const i64 *restrict aj = AT(a, acols, n, acol, j);
+    if (j < rsize) {
+      i64 *restrict rj = AT(res, rcols, n, rcol, j);
+      if (rj == aj) {  /* in place */
+        for (int i = 0; i < n; i++) {
+          const i64 t = rj[i] + cy[i], d = digit_l(k, t);
+          cy[i] = carry_l(k, t, d);
+          rj[i] = d;
+        }
+      } else {
+        for (int i = 0; i < n; i++) {
+          const i64 t = aj[i] + cy[i], d = digit_l(k, t);
+          cy[i] = carry_l(k, t, d);
+          rj[i] = d;
+        }
+      }
+    } else {
+      for (int i = 0; i < n; i++) {
+        const i64 t = aj[i] + cy[i];
+        cy[i] = carry_l(k, t, digit_l(k, t));
+      }
     }
   }
+  free(cy);
   for (int j = asize; j < rsize; j++) memset(AT(res, rcols, n, rcol, j), 0, sizeof(i64) * n);
 }
 
@@ -618,52 +735,67 @@ static void vz_rsh_inplace(int n, int K, int k, i64 *v, int cols, int col, int s
   }
   steps += 1;
   const int lsh = K - k_rem, bl = K - lsh;
-  for (int i = 0; i < n; i++) {
-    i64 carry = 0;
-    /* limbs shifted out: carry only */
-    for (int j = size - 1; j >= size - steps; j--) {
-      i64 x = AT(v, cols, n, col, j)[i];
-      i64 d = get_digit(bl, x), c0 = get_carry(bl, x, d);
-      if (j == size - 1) {
-        carry = c0;
-      } else {
-        i64 dpc = (d << lsh) + carry;
-        carry = c0 + get_carry(K, dpc, get_digit(K, dpc));
+  /* the same walk as Poulpy's (per coefficient: least significant limb first), limb by limb over all coefficients
+   * with the carries in an array so that the inner loops vectorise.  The limbs are read before they are
+   * overwritten: limb j is written from limb j - steps, walking j downwards. */
+  i64 *restrict cy = (i64 *)malloc(sizeof(i64) * (size_t)n);
+  /* limbs shifted out: carry only */
+  for (int j = size - 1; j >= size - steps; j--) {
+    const i64 *restrict vj = AT(v, cols, n, col, j);
+    if (j == size - 1) {
+      for (int i = 0; i < n; i++) {
+        const i64 x = vj[i];
+        cy[i] = carry_l(bl, x, digit_l(bl, x));
+      }
+    } else {
+      for (int i = 0; i < n; i++) {
+        const i64 x = vj[i], d = digit_l(bl, x), c0 = carry_l(bl, x, d);
+        const i64 dpc = (i64)((u64)d << lsh) + cy[i];
+        cy[i] = c0 + carry_l(K, dpc, digit_l(K, dpc));
       }
     }
-    /* shifted normalisation: res limb j from source limb j-steps */
-    for (int j = size - 1; j >= steps; j--) {
-      i64 x = AT(v, cols, n, col, j - steps)[i];
-      i64 d = get_digit(bl, x), c0 = get_carry(bl, x, d);
-      i64 dpc = (d << lsh) + carry;
-      i64 r = get_digit(K, dpc);
-      AT(v, cols, n, col, j)[i] = r;
-      carry = c0 + get_carry(K, dpc, r);
-    }
-    for (int j = steps - 1; j >= 0; j--) {
-      i64 r = get_digit(K, carry);
-      AT(v, cols, n, col, j)[i] = r;
-      carry = get_carry(K, carry, r);
+  }
+  /* shifted normalisation: res limb j from source limb j - steps */
+  for (int j = size - 1; j >= steps; j--) {
+    const i64 *restrict src = AT(v, cols, n, col, j - steps);
+    i64 *restrict dst = AT(v, cols, n, col, j);
+    for (int i = 0; i < n; i++) {
+      const i64 x = src[i], d = digit_l(bl, x), c0 = carry_l(bl, x, d);
+      const i64 dpc = (i64)((u64)d << lsh) + cy[i];
+      const i64 r = digit_l(K, dpc);
+      dst[i] = r;
+      cy[i] = c0 + carry_l(K, dpc, r);
     }
   }
+  for (int j = steps - 1; j >= 0; j--) {
+    i64 *restrict dst = AT(v, cols, n, col, j);
+    for (int i = 0; i < n; i++) {
+      const i64 r = digit_l(K, cy[i]);
+      dst[i] = r;
+      cy[i] = carry_l(K, cy[i], r);
+    }
+  }
+  free(cy);
 }
 
 /* Poulpy [spec] vec_znx_rotate: res = a * X^k in Z[X]/(X^n+1) (limb-wise, no renormalise) */
 static void poly_rotate(int n, i64 k, const i64 *a, i64 *res) {
   i64 two_n = 2 * (i64)n;
   i64 kk = ((k % two_n) + two_n) % two_n;
+  i64 e = kk;  /* (i + kk) mod 2n, 2n a power of two */
   for (int i = 0; i < n; i++) {
-    i64 e = (i + kk) % two_n;
     if (e >= n) res[e - n] = -a[i]; else res[e] = a[i];
+    e = (e + 1) & (two_n - 1);
   }
 }
 /* Poulpy [spec] vec_znx_automorphism: X^i -> X^(i*p) */
 static void poly_automorphism(int n, i64 p, const i64 *a, i64 *res) {
   i64 two_n = 2 * (i64)n;
   i64 pp = ((p % two_n) + two_n) % two_n;
+  i64 e = 0;  /* i * pp mod 2n, 2n a power of two */
   for (int i = 0; i < n; i++) {
-    i64 e = (i64)(((u128)(u64)i * (u64)pp) % (u64)two_n);
     if (e >= n) res[e - n] = -a[i]; else res[e] = a[i];
+    e = (e + pp) & (two_n - 1);
   }
 }
 
