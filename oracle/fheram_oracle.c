@@ -13,6 +13,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef __GLIBC__
+#include <malloc.h>
+#endif
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -614,6 +617,12 @@ static i64 mod_pow_i64(i64 b, u64 e, i64 m) {
 }
 
 orc_ctx *orc_ctx_new(const orc_params *p) {
+#if defined(__GLIBC__) && !defined(ORC_NO_MALLOPT)
+  /* the per-operation temporaries (192 - 256 KiB) are above glibc's default mmap threshold: every operation would map,
+   * fault in and unmap its buffers (a sixth of an external product).  Keep them on the heap. */
+  mallopt(M_MMAP_THRESHOLD, 64 << 20);
+  mallopt(M_TRIM_THRESHOLD, 256 << 20);
+#endif
   orc_ctx *c = (orc_ctx *)calloc(1, sizeof(*c));
   c->p = *p;
   c->log_n = p->log_n;
