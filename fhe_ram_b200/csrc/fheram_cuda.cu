@@ -184,7 +184,9 @@ struct DevBuf {
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
-    if (p) cudaFree(p);
+    // growing while kernels that read the old buffer may still be queued: wait for them explicitly (cudaFree would
+    // also synchronise the device, but the guarantee should not hang on an implementation detail of the allocator)
+    if (p) { cudaDeviceSynchronize(); cudaFree(p); }
     p = nullptr; bytes = 0;
     cudaError_t e = cudaMalloc(&p, need);
     if (e != cudaSuccess) return fail(FHERAM_ERR_CUDA, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
@@ -1352,11 +1354,16 @@ extern "C" int fheram_ram_load(fheram_ram* r, const int64_t* cts) {
   if (r->n_shards == 1) {
     TRY(upload_i64(c, cts, (size_t)ws * G * L, r->data));
   } else {
-    for (int s = 0; s < ws; s++)
+    // the rank's polynomials (h = shard + n_shards h') of one sub-RAM are gathered on the host and uploaded with one
+    // staged copy per sub-RAM (not one synchronous 192 KiB upload per polynomial: 4 096 of them at 2^22 x 4 B)
+    std::vector<int64_t> gathered((size_t)r->n_local * L);
+    for (int s = 0; s < ws; s++) {
       for (int hp = 0; hp < r->n_local; hp++) {
         const int h = r->shard + r->n_shards * hp;
-        TRY(upload_i64(c, cts + ((size_t)s * G + h) * L, L, r->data + ((size_t)s * r->n_local + hp) * L));
+        memcpy(gathered.data() + (size_t)hp * L, cts + ((size_t)s * G + h) * L, sizeof(int64_t) * L);
       }
+      TRY(upload_i64(c, gathered.data(), (size_t)r->n_local * L, r->data + (size_t)s * r->n_local * L));
+    }
   }
   r->loaded = true;
   r->state = false;
