@@ -398,8 +398,36 @@ static void tf_forward(const orc_ctx *c, const i64 *a, tfe *out, int mont) {
   (void)mont;
   const int m = c->n / 2;
   double *re = out, *im = out + m;
-  for (int i = 0; i < m; i++) { re[i] = i64_to_f64(a[i]); im[i] = i64_to_f64(a[i + m]); }
   int t = m, s = 1;
+  if ((t >> 2) >= 4) {
+    /* first pair of stages straight from the integer limbs: no separate conversion pass over the data (that pass
+     * alone cost more than a radix-4 pass: loads of a[] right behind stores to out[] at the same page offsets) */
+    const int q = t >> 2;
+    const double w1r = c->tw_re[1], w1i = c->tw_im[1];
+    const double w2r = c->tw_re[2], w2i = c->tw_im[2], w3r = c->tw_re[3], w3i = c->tw_im[3];
+    const i64 *restrict ar = a, *restrict ai = a + m;
+    double *restrict r0 = re, *restrict i0 = im;
+    double *restrict r1 = r0 + q, *restrict i1 = i0 + q, *restrict r2 = r0 + 2 * q, *restrict i2 = i0 + 2 * q,
+           *restrict r3 = r0 + 3 * q, *restrict i3 = i0 + 3 * q;
+#pragma GCC ivdep
+    for (int j = 0; j < q; j++) {
+      const double y0r = i64_to_f64(ar[j]), y0i = i64_to_f64(ai[j]);
+      const double y1r = i64_to_f64(ar[j + q]), y1i = i64_to_f64(ai[j + q]);
+      const double y2r = i64_to_f64(ar[j + 2 * q]), y2i = i64_to_f64(ai[j + 2 * q]);
+      const double y3r = i64_to_f64(ar[j + 3 * q]), y3i = i64_to_f64(ai[j + 3 * q]);
+      double pr = y2r * w1r - y2i * w1i, pi = y2r * w1i + y2i * w1r;
+      double br = y3r * w1r - y3i * w1i, bi = y3r * w1i + y3i * w1r;
+      double x0r = y0r + pr, x0i = y0i + pi, x2r = y0r - pr, x2i = y0i - pi;
+      double x1r = y1r + br, x1i = y1i + bi, x3r = y1r - br, x3i = y1i - bi;
+      double cr = x1r * w2r - x1i * w2i, ci = x1r * w2i + x1i * w2r;
+      double dr = x3r * w3r - x3i * w3i, di = x3r * w3i + x3i * w3r;
+      r0[j] = x0r + cr; i0[j] = x0i + ci; r1[j] = x0r - cr; i1[j] = x0i - ci;
+      r2[j] = x2r + dr; i2[j] = x2i + di; r3[j] = x2r - dr; i3[j] = x2i - di;
+    }
+    t = q; s = 4;
+  } else {
+    for (int i = 0; i < m; i++) { re[i] = i64_to_f64(a[i]); im[i] = i64_to_f64(a[i + m]); }
+  }
   /* fused pairs of stages (s, 2s) while the second stage still has distance >= 4 */
   for (; (t >> 2) >= 4; s <<= 2) {
     const int q = t >> 2; /* distance of the second stage; the block of 4q elements splits into quarters */
@@ -582,17 +610,22 @@ static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
     }
     t <<= 2;
   }
-  if (s == 1) { /* one stage left */
-    const double wr = c->tw_re[1], wi = -c->tw_im[1];
-    double *xr = re, *xi = im, *yr = re + t, *yi = im + t;
-    for (int j = 0; j < t; j++) {
-      double ur = xr[j], ui = xi[j], vr = yr[j], vi = yi[j];
-      xr[j] = ur + vr; xi[j] = ui + vi;
-      double dr = ur - vr, di = ui - vi;
-      yr[j] = dr * wr - di * wi; yi[j] = dr * wi + di * wr;
-    }
-  }
   const double sc = 1.0 / (double)m;
+  if (s == 1) { /* one stage left: fused with the scaling and the rounding to integers */
+    const double wr = c->tw_re[1], wi = -c->tw_im[1];
+    const double *restrict xr = re, *restrict xi = im, *restrict yr = re + t, *restrict yi = im + t;
+    i64 *restrict o = out;
+#pragma GCC ivdep
+    for (int j = 0; j < t; j++) {
+      const double ur = xr[j], ui = xi[j], vr = yr[j], vi = yi[j];
+      const double dr = ur - vr, di = ui - vi;
+      o[j] = f64_round_i64((ur + vr) * sc);
+      o[j + m] = f64_round_i64((ui + vi) * sc);
+      o[j + t] = f64_round_i64((dr * wr - di * wi) * sc);
+      o[j + t + m] = f64_round_i64((dr * wi + di * wr) * sc);
+    }
+    return;
+  }
   for (int i = 0; i < m; i++) {
     out[i] = f64_round_i64(re[i] * sc);
     out[i + m] = f64_round_i64(im[i] * sc);
