@@ -537,36 +537,52 @@ static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
   double *re = a, *im = a + m;
   int t = 1, s = m >> 1;
 #ifdef __AVX2__
-  if (m >= 8) {
-    /* first two stages (distances 1 and 2) in registers, four points per vector */
+  if (m >= 16) {
+    /* first three stages (distances 1, 2, 4) in registers, one block of 8 points per iteration */
     const double *w1r = c->tw_re + s, *w1i = c->tw_im + s;          /* one twiddle per pair */
     const double *w2r = c->tw_re + s / 2, *w2i = c->tw_im + s / 2;  /* one per block of four */
-    for (int b = 0; b < m / 4; b++) {
-      __m256d R = _mm256_loadu_pd(re + 4 * b), I = _mm256_loadu_pd(im + 4 * b);
-      { /* distance 1: (x, y) <- (x + y, (x - y) conj(w)) */
-        const __m256d wr = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1r + 2 * b)), 0x50);
-        const __m256d wi = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1i + 2 * b)), 0x50);
-        const __m256d ur = _mm256_permute_pd(R, 0x0), yr = _mm256_permute_pd(R, 0xF);
-        const __m256d ui = _mm256_permute_pd(I, 0x0), yi = _mm256_permute_pd(I, 0xF);
-        const __m256d sr = _mm256_add_pd(ur, yr), si = _mm256_add_pd(ui, yi);
-        const __m256d dr = _mm256_sub_pd(ur, yr), di = _mm256_sub_pd(ui, yi);
-        const __m256d pr = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));   /* dr wr + di wi */
-        const __m256d pi = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr));  /* di wr - dr wi */
-        R = _mm256_blend_pd(sr, pr, 0xA); I = _mm256_blend_pd(si, pi, 0xA);
+    const double *w4r = c->tw_re + s / 4, *w4i = c->tw_im + s / 4;  /* one per block of eight */
+#define ORC_INV_D1(R, I, K)                                                                                          \
+      { /* distance 1: (x, y) <- (x + y, (x - y) conj(w)) */                                                         \
+        const __m256d wr = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1r + 4 * b + 2 * (K))), 0x50); \
+        const __m256d wi = _mm256_permute4x64_pd(_mm256_castpd128_pd256(_mm_loadu_pd(w1i + 4 * b + 2 * (K))), 0x50); \
+        const __m256d ur = _mm256_permute_pd(R, 0x0), yr = _mm256_permute_pd(R, 0xF);                                \
+        const __m256d ui = _mm256_permute_pd(I, 0x0), yi = _mm256_permute_pd(I, 0xF);                                \
+        const __m256d sr = _mm256_add_pd(ur, yr), si = _mm256_add_pd(ui, yi);                                        \
+        const __m256d dr = _mm256_sub_pd(ur, yr), di = _mm256_sub_pd(ui, yi);                                        \
+        const __m256d pr = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));  /* dr wr + di wi */                      \
+        const __m256d pi = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr)); /* di wr - dr wi */                      \
+        R = _mm256_blend_pd(sr, pr, 0xA); I = _mm256_blend_pd(si, pi, 0xA);                                          \
       }
-      { /* distance 2 */
-        const __m256d wr = _mm256_broadcast_sd(w2r + b), wi = _mm256_broadcast_sd(w2i + b);
-        const __m256d ur = _mm256_permute2f128_pd(R, R, 0x00), yr = _mm256_permute2f128_pd(R, R, 0x11);
-        const __m256d ui = _mm256_permute2f128_pd(I, I, 0x00), yi = _mm256_permute2f128_pd(I, I, 0x11);
-        const __m256d sr = _mm256_add_pd(ur, yr), si = _mm256_add_pd(ui, yi);
-        const __m256d dr = _mm256_sub_pd(ur, yr), di = _mm256_sub_pd(ui, yi);
-        const __m256d pr = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));
-        const __m256d pi = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr));
-        R = _mm256_blend_pd(sr, pr, 0xC); I = _mm256_blend_pd(si, pi, 0xC);
+#define ORC_INV_D2(R, I, K)                                                                                          \
+      {                                                                                                              \
+        const __m256d wr = _mm256_broadcast_sd(w2r + 2 * b + (K)), wi = _mm256_broadcast_sd(w2i + 2 * b + (K));      \
+        const __m256d ur = _mm256_permute2f128_pd(R, R, 0x00), yr = _mm256_permute2f128_pd(R, R, 0x11);              \
+        const __m256d ui = _mm256_permute2f128_pd(I, I, 0x00), yi = _mm256_permute2f128_pd(I, I, 0x11);              \
+        const __m256d sr = _mm256_add_pd(ur, yr), si = _mm256_add_pd(ui, yi);                                        \
+        const __m256d dr = _mm256_sub_pd(ur, yr), di = _mm256_sub_pd(ui, yi);                                        \
+        const __m256d pr = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));                                           \
+        const __m256d pi = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr));                                          \
+        R = _mm256_blend_pd(sr, pr, 0xC); I = _mm256_blend_pd(si, pi, 0xC);                                          \
       }
-      _mm256_storeu_pd(re + 4 * b, R); _mm256_storeu_pd(im + 4 * b, I);
+    for (int b = 0; b < m / 8; b++) {
+      __m256d R0 = _mm256_loadu_pd(re + 8 * b), R1 = _mm256_loadu_pd(re + 8 * b + 4);
+      __m256d I0 = _mm256_loadu_pd(im + 8 * b), I1 = _mm256_loadu_pd(im + 8 * b + 4);
+      ORC_INV_D1(R0, I0, 0)
+      ORC_INV_D1(R1, I1, 1)
+      ORC_INV_D2(R0, I0, 0)
+      ORC_INV_D2(R1, I1, 1)
+      { /* distance 4 */
+        const __m256d wr = _mm256_broadcast_sd(w4r + b), wi = _mm256_broadcast_sd(w4i + b);
+        const __m256d dr = _mm256_sub_pd(R0, R1), di = _mm256_sub_pd(I0, I1);
+        R0 = _mm256_add_pd(R0, R1); I0 = _mm256_add_pd(I0, I1);
+        R1 = _mm256_fmadd_pd(di, wi, _mm256_mul_pd(dr, wr));
+        I1 = _mm256_fnmadd_pd(dr, wi, _mm256_mul_pd(di, wr));
+      }
+      _mm256_storeu_pd(re + 8 * b, R0); _mm256_storeu_pd(re + 8 * b + 4, R1);
+      _mm256_storeu_pd(im + 8 * b, I0); _mm256_storeu_pd(im + 8 * b + 4, I1);
     }
-    t = 4; s >>= 2;
+    t = 8; s >>= 3;
   }
 #endif
   /* single stages while the distance is below 4 */
@@ -583,9 +599,32 @@ static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
     }
     t <<= 1;
   }
+  const double sc = 1.0 / (double)m;
   /* fused pairs of stages (s, s / 2): distance t then 2t */
   for (; s >= 2; s >>= 2) {
     const int h = s >> 1; /* blocks of the second stage */
+    if (s == 2) {
+      /* the last pair: scaled and rounded straight into the integer result (no separate pass) */
+      const double w2r = c->tw_re[2], w2i = -c->tw_im[2], w3r = c->tw_re[3], w3i = -c->tw_im[3];
+      const double w1r = c->tw_re[1], w1i = -c->tw_im[1];
+      const double *restrict r0 = re, *restrict i0 = im;
+      const double *restrict r1 = r0 + t, *restrict i1 = i0 + t, *restrict r2 = r0 + 2 * t, *restrict i2 = i0 + 2 * t,
+                   *restrict r3 = r0 + 3 * t, *restrict i3 = i0 + 3 * t;
+      i64 *restrict o = out;
+#pragma GCC ivdep
+      for (int j = 0; j < t; j++) {
+        double x0r = r0[j] + r1[j], x0i = i0[j] + i1[j], d0r = r0[j] - r1[j], d0i = i0[j] - i1[j];
+        double x2r = r2[j] + r3[j], x2i = i2[j] + i3[j], d1r = r2[j] - r3[j], d1i = i2[j] - i3[j];
+        double x1r = d0r * w2r - d0i * w2i, x1i = d0r * w2i + d0i * w2r;
+        double x3r = d1r * w3r - d1i * w3i, x3i = d1r * w3i + d1i * w3r;
+        double e0r = x0r - x2r, e0i = x0i - x2i, e1r = x1r - x3r, e1i = x1i - x3i;
+        o[j] = f64_round_i64((x0r + x2r) * sc); o[j + m] = f64_round_i64((x0i + x2i) * sc);
+        o[j + t] = f64_round_i64((x1r + x3r) * sc); o[j + t + m] = f64_round_i64((x1i + x3i) * sc);
+        o[j + 2 * t] = f64_round_i64((e0r * w1r - e0i * w1i) * sc); o[j + 2 * t + m] = f64_round_i64((e0r * w1i + e0i * w1r) * sc);
+        o[j + 3 * t] = f64_round_i64((e1r * w1r - e1i * w1i) * sc); o[j + 3 * t + m] = f64_round_i64((e1r * w1i + e1i * w1r) * sc);
+      }
+      return;
+    }
     for (int b = 0; b < h; b++) {
       const double w2r = c->tw_re[s + 2 * b], w2i = -c->tw_im[s + 2 * b];
       const double w3r = c->tw_re[s + 2 * b + 1], w3i = -c->tw_im[s + 2 * b + 1];
@@ -610,7 +649,6 @@ static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
     }
     t <<= 2;
   }
-  const double sc = 1.0 / (double)m;
   if (s == 1) { /* one stage left: fused with the scaling and the rounding to integers */
     const double wr = c->tw_re[1], wi = -c->tw_im[1];
     const double *restrict xr = re, *restrict xi = im, *restrict yr = re + t, *restrict yi = im + t;
