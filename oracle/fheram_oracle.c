@@ -531,6 +531,27 @@ static void tf_mac(const orc_ctx *c, tfe *acc, const tfe *a, const tfe *b) {
     acc[i + m] += ar * bi + ai * br;
   }
 }
+/* acc = sum_k a[k] * b[k] (complex, pointwise), terms added in index order starting from zero: one pass over the
+ * accumulator instead of tf_zero + cnt x tf_mac */
+static void tf_dot(const orc_ctx *c, tfe *restrict acc, const tfe *const *a, const tfe *const *b, int cnt) {
+  const int m = c->n / 2;
+#ifdef __AVX2__
+  for (int i = 0; i < m; i += 4) {
+    __m256d sr = _mm256_setzero_pd(), si = _mm256_setzero_pd();
+    for (int k = 0; k < cnt; k++) {
+      const __m256d ar = _mm256_loadu_pd(a[k] + i), ai = _mm256_loadu_pd(a[k] + i + m);
+      const __m256d br = _mm256_loadu_pd(b[k] + i), bi = _mm256_loadu_pd(b[k] + i + m);
+      sr = _mm256_add_pd(sr, _mm256_fnmadd_pd(ai, bi, _mm256_mul_pd(ar, br)));
+      si = _mm256_add_pd(si, _mm256_fmadd_pd(ai, br, _mm256_mul_pd(ar, bi)));
+    }
+    _mm256_storeu_pd(acc + i, sr);
+    _mm256_storeu_pd(acc + i + m, si);
+  }
+#else
+  tf_zero(c, acc);
+  for (int k = 0; k < cnt; k++) tf_mac(c, acc, a[k], b[k]);
+#endif
+}
 ORC_CLONES
 static void tf_inverse(const orc_ctx *c, tfe *a, i64 *out) {
   const int m = c->n / 2;
@@ -966,12 +987,25 @@ static void vmp_apply(const orc_ctx *c, const i64 *a, int a_cols, int a_size, in
   tfe *acc = (tfe *)malloc(sizeof(tfe) * n);
   for (int co = 0; co < m->cols_out; co++)
     for (int l = 0; l < m->size; l++) {
+#ifdef ORC_FFT64
+      const tfe *pa[32], *pb[32];
+      int cnt = 0;
+      for (int r = 0; r < rows; r++)
+        for (int ci = 0; ci < m->cols_in; ci++) {
+          size_t idx = (((size_t)r * m->cols_in + ci) * m->cols_out + co) * m->size + l;
+          pa[cnt] = atf + ((size_t)r * m->cols_in + ci) * n;
+          pb[cnt] = m->d + idx * n;
+          cnt++;
+        }
+      tf_dot(c, acc, pa, pb, cnt);
+#else
       tf_zero(c, acc);
       for (int r = 0; r < rows; r++)
         for (int ci = 0; ci < m->cols_in; ci++) {
           size_t idx = (((size_t)r * m->cols_in + ci) * m->cols_out + co) * m->size + l;
           tf_mac(c, acc, atf + ((size_t)r * m->cols_in + ci) * n, m->d + idx * n);
         }
+#endif
       tf_inverse(c, acc, AT(big, m->cols_out, n, co, l));
     }
   free(acc);
